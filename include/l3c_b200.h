@@ -1,0 +1,200 @@
+/*
+ * l3c_b200.h -- C ABI of libl3c_b200.so: the sm_100a implementation of L3C's encode/decode hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  Every entry point returns 0 on success or a
+ * negative L3C_E* code; l3c_last_error() gives the message of the last failure on the calling
+ * thread.  "dev" pointers are CUDA device pointers on the current device, "host" pointers are
+ * ordinary (ideally pinned) host memory.  `stream` is a cudaStream_t passed as void* (NULL = the
+ * legacy default stream).  Kernels are asynchronous on `stream` unless a function says it
+ * synchronises.
+ *
+ * Section A are the drop-in replacements for the FIVE exports of the reference's native module
+ * (pybind module torchac_backend_{cpu,gpu}: /root/reference/src/torchac/torchac_backend/
+ * torchac.cpp:433-443).  Sections B..E are the batched, device-resident building blocks the host
+ * mirror (l3c_pytorch_b200.*) composes into the reference's Bitcoding / MultiscaleBlueprint API.
+ *
+ * Layout conventions
+ *   activations ........ NHWC fp32, channel pitch given explicitly where slices are written
+ *   conv weights ....... [KH][KW][Cin][CoutPad] fp32 (host mirror repacks the reference's OIHW)
+ *   symbol planes ...... uint8  [N][C][H*W]    (one plane = one coded stream, row-major H,W;
+ *                                               flatten order of coders.py:49-50)
+ *   intervals .......... uint32 [N][C][H*W]    c_low | (c_high-1) << 16
+ *   CDF tables ......... uint16 rows of `pitch` entries (entries 0..L-1 used; the reference's
+ *                        (L+1)-th entry is never read, torchac.cpp:181,280)
+ */
+#ifndef L3C_B200_H_
+#define L3C_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define L3C_OK 0
+#define L3C_EINVAL (-1)   /* bad argument (shape/alignment/range)      -> reference raises RuntimeError */
+#define L3C_ECUDA (-2)    /* CUDA runtime error                                                          */
+#define L3C_EOVERFLOW (-3)/* output buffer too small                                                     */
+#define L3C_ENODEV (-4)   /* no sm_100 device                                                            */
+
+const char *l3c_last_error(void);
+int l3c_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * A. Drop-in native exports (reference: torchac.cpp:433-443; python shim torchac.py:87-166)
+ * ---------------------------------------------------------------------------------------- */
+
+/* replaces `cuda_supported()` (torchac.cpp:439,441): 1 iff an sm_100 device is usable. */
+int l3c_cuda_supported(void);
+
+/* replaces `encode_cdf(cdf, sym) -> bytes` (torchac.cpp:262-269 -> encode() :152-227).
+ * cdf_host: int16/uint16 [n_sym][Lp] (the 1HWLp tensor, flattened); sym_host: int16 [n_sym].
+ * Synchronous.  *out_len receives the byte count; L3C_EOVERFLOW if it exceeds out_cap. */
+int l3c_encode_cdf(const uint16_t *cdf_host, int64_t n_sym, int Lp, const int16_t *sym_host,
+                   uint8_t *out_host, size_t out_cap, size_t *out_len);
+
+/* replaces `decode_cdf(cdf, in) -> int16 tensor` (torchac.cpp:424-430 -> decode() :299-381).
+ * n_sym comes from the cdf shape, exactly as in the reference; short input is zero-filled. */
+int l3c_decode_cdf(const uint16_t *cdf_host, int64_t n_sym, int Lp, const uint8_t *in_host,
+                   size_t in_len, int16_t *sym_out_host);
+
+/* replaces `encode_logistic_mixture(targets, means, log_scales, logit_probs_softmax, sym)`
+ * (torchac.cpp:231-258; CDF formula torchac_kernel.cu:20-76).  targets_dev f32[Lp];
+ * means/log_scales/probs_dev f32 [K][n_sym] (1KHW contiguous, CUDA); sym_host int16 (CPU, as in
+ * the reference).  No CDF table is materialised: only the two bounds of each coded symbol are
+ * evaluated.  Synchronous. */
+int l3c_encode_logistic_mixture(const float *targets_dev, const float *means_dev,
+                                const float *log_scales_dev, const float *probs_dev, int K,
+                                int64_t n_sym, int Lp, const int16_t *sym_host,
+                                uint8_t *out_host, size_t out_cap, size_t *out_len);
+
+/* replaces `decode_logistic_mixture(..., in) -> int16 tensor` (torchac.cpp:385-421). */
+int l3c_decode_logistic_mixture(const float *targets_dev, const float *means_dev,
+                                const float *log_scales_dev, const float *probs_dev, int K,
+                                int64_t n_sym, int Lp, const uint8_t *in_host, size_t in_len,
+                                int16_t *sym_out_host);
+
+/* ------------------------------------------------------------------------------------------
+ * B. Range coder, batched: one warp per stream, any number of streams per launch
+ *    (reference loop: torchac.cpp:174-207 encode, :325-373 decode, one stream per call)
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct {
+    const uint32_t *intervals;  /* dev: n_sym packed intervals                                  */
+    uint8_t *out;               /* dev: output slot, 4-byte aligned, out_cap bytes              */
+    uint32_t n_sym;
+    uint32_t out_cap;           /* multiple of 4                                                */
+} l3c_enc_stream_t;
+
+/* out_len_dev[i] = bytes produced by stream i (if > out_cap the slot content is truncated). */
+int l3c_ac_encode_streams(const l3c_enc_stream_t *streams_dev, int n_streams,
+                          uint32_t *out_len_dev, void *stream);
+
+typedef struct {
+    const uint16_t *table;      /* dev: CDF rows for symbols [0, n_sym) of this stream           */
+    const uint8_t *in;          /* dev: code bytes, 4-byte aligned, readable up to in_len        */
+    uint8_t *sym_out;           /* dev: n_sym decoded symbols                                    */
+    uint32_t *state;            /* dev: 4 words of coder state (low, high, value, bitpos);        */
+                                /*      lets one stream be decoded in several launches (chunks)   */
+    int64_t row_pitch;          /* entries between consecutive rows; 0 = one shared row           */
+    uint32_t n_sym;             /* total symbols of the stream                                    */
+    uint32_t in_len;
+} l3c_dec_stream_t;
+
+/* Decodes symbols [first, first+count) of every stream (count clipped to n_sym).  first == 0
+ * initialises the coder state from the stream head, otherwise it is resumed from `state`.
+ * L = number of symbols of the alphabet (<= 256). */
+int l3c_ac_decode_streams(const l3c_dec_stream_t *streams_dev, int n_streams, int L,
+                          uint32_t first, uint32_t count, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * C. Discretised-logistic-mixture head
+ *    (reference: criterion/logistic_mixture.py:134-275, torchac.py:174-213,
+ *     torchac_kernel.cu:20-76, bitcoding.py:297-323)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Shared CDF row of the uniform prior (bitcoding.py:297-323): L+1 uint16 entries written to
+ * row_host (host-side helper, no device work). */
+int l3c_uniform_cdf_row(int L, uint16_t *row_host);
+
+/* Per-symbol coding intervals for all C channels of one scale of a batch.
+ *   l_dev      f32 NHWC [N][HW][Kp], Kp = (rgb ? 4 : 3) * C * K, channel index p*C*K + c*K + k
+ *   sym_dev    uint8 [N][C][HW]  symbols being coded (also supply the RGB coupling values)
+ *   values_dev f32 [L] value of each symbol (0..255 for RGB, the quantiser levels otherwise);
+ *              only used for the RGB mean coupling
+ *   targets_dev f32 [L+1] bin edges (coders_helpers.py:44-46)
+ *   intervals_dev uint32 [N][C][HW] out */
+int l3c_dmll_intervals(const float *l_dev, const uint8_t *sym_dev, const float *targets_dev,
+                       int N, int HW, int C, int K, int L, int rgb, uint32_t *intervals_dev,
+                       void *stream);
+
+/* uint16 CDF rows (pitch entries each, pitch >= L, multiple of 8) for channel c of pixels
+ * [pix0, pix0+npix) of every image: table_dev[(n*HW + p) * pitch + l].  For rgb && c > 0 the
+ * already decoded channels are read from sym_dev. */
+int l3c_dmll_build_table(const float *l_dev, const uint8_t *sym_dev, const float *targets_dev,
+                         int N, int HW, int C, int K, int L, int rgb, int c, int pix0, int npix,
+                         uint16_t *table_dev, int pitch, void *stream);
+
+/* Negative log-likelihood (nats) summed per image: nll_dev f64 [N] (overwritten).
+ * target value of symbol s is values_dev[s] (logistic_mixture.py:146-207). */
+int l3c_dmll_nll(const float *l_dev, const uint8_t *sym_dev, const float *values_dev,
+                 int N, int HW, int C, int K, int L, int rgb, float x_min, float x_max,
+                 double *nll_dev, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * D. Convolution stack (reference: modules/net.py:89-184, edsr.py:52-119, head.py:26-59,
+ *    prob_clf.py:29-74, pytorch_ext.py:57-61; all nn.Conv2d fp32)
+ * ---------------------------------------------------------------------------------------- */
+
+#define L3C_CONV_RELU 1u            /* y = max(y, 0) after bias                                  */
+#define L3C_CONV_PIXEL_SHUFFLE2 2u  /* out[n,2h+i,2w+j,c] = y[n,h,w,4c+2i+j] (edsr.py:92-101)     */
+
+#define L3C_PREC_FP32 0             /* CUDA-core FFMA, fp32 throughout (bit-faithful ordering)    */
+#define L3C_PREC_TF32 1             /* tcgen05 kind::tf32, fp32 accumulate in TMEM                */
+#define L3C_PREC_TF32X3 2           /* tcgen05, error-compensated 3xTF32 split (~fp32 accuracy)   */
+#define L3C_PREC_BF16 3             /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate         */
+
+typedef struct {
+    const float *x;        /* dev NHWC [N][H][W][x_pitch], channels [0,Cin) read                  */
+    const float *w;        /* dev [KH][KW][Cin][cout_pad]                                          */
+    const float *bias;     /* dev [cout_pad]                                                       */
+    const float *residual; /* dev NHWC like the output (same pitch/offset), or NULL: y += res      */
+    float *y;              /* dev NHWC [N][Ho][Wo][y_pitch], channels [y_coff, y_coff+Cout) written */
+    int N, H, W, Cin, x_pitch;
+    int Cout, cout_pad, y_pitch, y_coff;
+    int ksize, stride, dilation;   /* padding = ksize/2 if dilation==1 else dilation               */
+    unsigned flags;
+    int precision;
+} l3c_conv_t;
+
+int l3c_conv2d(const l3c_conv_t *p, void *stream);
+
+/* sub_rgb_mean + first MeanShift of RGBHead as one per-pixel 3x3 affine pair
+ * (multiscale_network.py:181-183, head.py:31-33): img uint8 [N][3][HW] planes ->
+ * x_sub f32 NHWC [N][HW][3] (= A1 img + b1)  and  t f32 NHWC [N][HW][4] (= A2 x_sub + b2, ch 3 = 0).
+ * A1,b1,A2,b2: dev f32 [9],[3],[9],[3] (the two 1x1 conv parameter sets). Either output may be NULL. */
+int l3c_rgb_prep(const uint8_t *img_dev, const float *A1, const float *b1, const float *A2,
+                 const float *b2, int N, int HW, float *xsub_dev, float *t_dev, void *stream);
+
+/* to_q 1x1 conv + hard quantiser (net.py:116-148, quantizer.py:62-90):
+ * sym = argmin_l (q - level_l)^2 (first minimum), bn_q = levels[sym].
+ * f_dev NHWC [N][HW][Cf]; w_dev [Cf][C]; bias [C]; levels [L];
+ * sym_dev uint8 [N][C][HW] planes; bnq_dev f32 NHWC [N][HW][C]. */
+int l3c_quantize_head(const float *f_dev, const float *w_dev, const float *bias_dev,
+                      const float *levels_dev, int N, int HW, int Cf, int C, int L,
+                      uint8_t *sym_dev, float *bnq_dev, void *stream);
+
+/* bn = values[sym] for symbol planes -> NHWC f32 [N][HW][C] minus optional per-channel shift
+ * (decode side of quantizer.py:44-47 / SURVEY finding 1, and the RGB baselines' x - rgb_mean). */
+int l3c_symbols_to_values(const uint8_t *sym_dev, const float *values_dev, const float *shift_dev,
+                          int N, int HW, int C, int L, float *out_dev, void *stream);
+
+/* Pillow-compatible bicubic x0.5 on uint8 planes [N][3][H][W] -> [N][3][H/2][W/2]
+ * (dataloaders/images_loader.py:277-293 via PIL.Image.resize(BICUBIC); RGB baselines only). */
+int l3c_bicubic_half_u8(const uint8_t *in_dev, int N, int H, int W, uint8_t *out_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* L3C_B200_H_ */

@@ -1,0 +1,270 @@
+// capi.cu -- error plumbing, dispatch and the five drop-in exports of the reference's native module
+// (torchac_backend_{cpu,gpu}: /root/reference/src/torchac/torchac_backend/torchac.cpp:433-443),
+// implemented on top of the batched kernels of range_coder.cu / dmll.cu.
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace l3c {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int conv2d_ffma(const l3c_conv_t &p, cudaStream_t st);
+int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st);
+
+// ---- helper kernels for the single-stream (reference-shaped) API -----------------------------
+
+// intervals from an explicit table: torchac.cpp:178-182
+__global__ void table_intervals_kernel(const uint16_t *__restrict__ cdf, const int16_t *__restrict__ sym,
+                                       int64_t n_sym, int Lp, uint32_t *__restrict__ iv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sym) return;
+    const int s = sym[i];
+    const uint32_t lo = cdf[i * Lp + s];
+    const uint32_t hi = (s == Lp - 2) ? 0x10000u : (uint32_t)cdf[i * Lp + s + 1];
+    iv[i] = lo | ((hi - 1u) << 16);
+}
+
+// [n][Lp] rows -> [n][pitch] rows (the dead (L+1)-th entry is dropped, the tail is padding)
+__global__ void repitch_kernel(const uint16_t *__restrict__ cdf, int64_t n_sym, int Lp, int pitch,
+                               uint16_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sym * pitch) return;
+    const int64_t r = i / pitch;
+    const int e = (int)(i % pitch);
+    out[i] = (e < Lp - 1) ? cdf[r * Lp + e] : (uint16_t)0;
+}
+
+__device__ __forceinline__ float sigmoid_rn(float a) {
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-a)));
+}
+
+// cdf[n][l] of torchac_kernel.cu:58-75 with parameters given as [K][N] planes
+__device__ __forceinline__ uint32_t plane_cdf_u16(const float *__restrict__ means,
+                                                  const float *__restrict__ log_scales,
+                                                  const float *__restrict__ probs, int K, int64_t N,
+                                                  int64_t n, float target, float scale, int l) {
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const float inv = expf(-log_scales[k * N + n]);
+        const float a = __fmul_rn(__fsub_rn(target, means[k * N + n]), inv);
+        acc = __fadd_rn(acc, __fmul_rn(probs[k * N + n], sigmoid_rn(a)));
+    }
+    return (uint32_t)(__float2int_rn(__fmul_rn(acc, scale)) + l) & 0xFFFFu;
+}
+
+__global__ void plane_intervals_kernel(const float *__restrict__ targets, const float *__restrict__ means,
+                                       const float *__restrict__ log_scales,
+                                       const float *__restrict__ probs, int K, int64_t N, int Lp,
+                                       const int16_t *__restrict__ sym, uint32_t *__restrict__ iv) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int s = sym[n];
+    const float scale = (float)(65536 - (Lp - 1));
+    const uint32_t lo = plane_cdf_u16(means, log_scales, probs, K, N, n, targets[s], scale, s);
+    const uint32_t hi = (s == Lp - 2) ? 0x10000u
+                                      : plane_cdf_u16(means, log_scales, probs, K, N, n,
+                                                      targets[s + 1], scale, s + 1);
+    iv[n] = lo | ((hi - 1u) << 16);
+}
+
+__global__ void plane_table_kernel(const float *__restrict__ targets, const float *__restrict__ means,
+                                   const float *__restrict__ log_scales,
+                                   const float *__restrict__ probs, int K, int64_t N, int Lp, int pitch,
+                                   uint16_t *__restrict__ table) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * pitch) return;
+    const int64_t n = i / pitch;
+    const int l = (int)(i % pitch);
+    uint32_t v = 0;
+    if (l < Lp - 1)
+        v = plane_cdf_u16(means, log_scales, probs, K, N, n, targets[l], (float)(65536 - (Lp - 1)), l);
+    table[i] = (uint16_t)v;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t bytes) {
+        L3C_CUDA(cudaMalloc(&p, bytes ? bytes : 4));
+        return L3C_OK;
+    }
+    template <typename T>
+    T *as() { return reinterpret_cast<T *>(p); }
+};
+
+static int run_encode(const uint32_t *iv_dev, int64_t n_sym, uint8_t *out_host, size_t out_cap,
+                      size_t *out_len) {
+    const size_t cap = (((size_t)n_sym * 17 + 7) / 8 + 64 + 3) & ~(size_t)3;
+    DevBuf out, desc, len;
+    if (int e = out.alloc(cap)) return e;
+    if (int e = desc.alloc(sizeof(l3c_enc_stream_t))) return e;
+    if (int e = len.alloc(4)) return e;
+    l3c_enc_stream_t d;
+    d.intervals = iv_dev;
+    d.out = out.as<uint8_t>();
+    d.n_sym = (uint32_t)n_sym;
+    d.out_cap = (uint32_t)cap;
+    L3C_CUDA(cudaMemcpy(desc.p, &d, sizeof(d), cudaMemcpyHostToDevice));
+    if (int e = l3c_ac_encode_streams(desc.as<l3c_enc_stream_t>(), 1, len.as<uint32_t>(), nullptr)) return e;
+    uint32_t n = 0;
+    L3C_CUDA(cudaMemcpy(&n, len.p, 4, cudaMemcpyDeviceToHost));
+    *out_len = n;
+    if (n > out_cap || n > cap) {
+        set_error("encode: %u bytes do not fit the %zu byte output buffer", n, out_cap);
+        return L3C_EOVERFLOW;
+    }
+    L3C_CUDA(cudaMemcpy(out_host, out.p, n, cudaMemcpyDeviceToHost));
+    return L3C_OK;
+}
+
+static int run_decode(const uint16_t *table_dev, int pitch, int64_t n_sym, int L,
+                      const uint8_t *in_host, size_t in_len, int16_t *sym_out_host) {
+    const size_t padded = ((in_len + 3) & ~(size_t)3) + 8;
+    DevBuf in, sym, desc;
+    if (int e = in.alloc(padded)) return e;
+    if (int e = sym.alloc((size_t)n_sym)) return e;
+    if (int e = desc.alloc(sizeof(l3c_dec_stream_t))) return e;
+    L3C_CUDA(cudaMemset(in.p, 0, padded));
+    if (in_len) L3C_CUDA(cudaMemcpy(in.p, in_host, in_len, cudaMemcpyHostToDevice));
+    l3c_dec_stream_t d;
+    d.table = table_dev;
+    d.in = in.as<uint8_t>();
+    d.sym_out = sym.as<uint8_t>();
+    d.state = nullptr;
+    d.row_pitch = pitch;
+    d.n_sym = (uint32_t)n_sym;
+    d.in_len = (uint32_t)in_len;
+    L3C_CUDA(cudaMemcpy(desc.p, &d, sizeof(d), cudaMemcpyHostToDevice));
+    if (int e = l3c_ac_decode_streams(desc.as<l3c_dec_stream_t>(), 1, L, 0, (uint32_t)n_sym, nullptr)) return e;
+    std::vector<uint8_t> tmp((size_t)n_sym);
+    L3C_CUDA(cudaMemcpy(tmp.data(), sym.p, (size_t)n_sym, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n_sym; ++i) sym_out_host[i] = (int16_t)tmp[(size_t)i];
+    return L3C_OK;
+}
+
+static int check_stream_args(const char *fn, int64_t n_sym, int Lp) {
+    L3C_REQUIRE(n_sym >= 1 && n_sym < (1ll << 31), "%s: n_sym=%lld", fn, (long long)n_sym);
+    L3C_REQUIRE(Lp >= 2 && Lp <= 257, "%s: Lp=%d not in [2,257]", fn, Lp);
+    return L3C_OK;
+}
+
+}  // namespace l3c
+
+using namespace l3c;
+
+extern "C" const char *l3c_last_error(void) { return g_err; }
+extern "C" int l3c_version(void) { return 100; }
+
+extern "C" int l3c_cuda_supported(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return 0;
+    }
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10 ? 1 : 0;
+}
+
+extern "C" int l3c_conv2d(const l3c_conv_t *p, void *stream) {
+    L3C_REQUIRE(p && p->x && p->w && p->bias && p->y, "l3c_conv2d: null pointer");
+    L3C_REQUIRE(p->N >= 1 && p->N <= 65535 && p->H >= 1 && p->W >= 1, "l3c_conv2d: N=%d H=%d W=%d", p->N, p->H, p->W);
+    L3C_REQUIRE(p->Cin >= 1 && p->x_pitch >= p->Cin && p->x_pitch % 4 == 0,
+                "l3c_conv2d: Cin=%d x_pitch=%d (pitch must be a multiple of 4)", p->Cin, p->x_pitch);
+    L3C_REQUIRE(p->Cout >= 1 && p->cout_pad >= p->Cout && p->cout_pad % 64 == 0,
+                "l3c_conv2d: Cout=%d cout_pad=%d (must be padded to a multiple of 64)", p->Cout, p->cout_pad);
+    L3C_REQUIRE(p->dilation >= 1 && (p->dilation == 1 || p->ksize == 3), "l3c_conv2d: dilation=%d ksize=%d", p->dilation, p->ksize);
+    if (p->flags & L3C_CONV_PIXEL_SHUFFLE2) {
+        L3C_REQUIRE(p->Cout % 4 == 0 && p->y_pitch >= p->y_coff + p->Cout / 4, "l3c_conv2d: pixel-shuffle pitch");
+    } else {
+        L3C_REQUIRE(p->y_pitch >= p->y_coff + p->Cout, "l3c_conv2d: y_pitch=%d y_coff=%d Cout=%d", p->y_pitch, p->y_coff, p->Cout);
+    }
+    if (p->precision == L3C_PREC_FP32) return conv2d_ffma(*p, (cudaStream_t)stream);
+    return conv2d_tcgen05(*p, (cudaStream_t)stream);
+}
+
+extern "C" int l3c_encode_cdf(const uint16_t *cdf_host, int64_t n_sym, int Lp,
+                              const int16_t *sym_host, uint8_t *out_host, size_t out_cap,
+                              size_t *out_len) {
+    if (int e = check_stream_args("l3c_encode_cdf", n_sym, Lp)) return e;
+    L3C_REQUIRE(cdf_host && sym_host && out_host && out_len, "l3c_encode_cdf: null pointer");
+    for (int64_t i = 0; i < n_sym; ++i)
+        L3C_REQUIRE(sym_host[i] >= 0 && sym_host[i] <= Lp - 2, "l3c_encode_cdf: symbol %d at %lld outside [0,%d]",
+                    (int)sym_host[i], (long long)i, Lp - 2);
+    DevBuf cdf, sym, iv;
+    if (int e = cdf.alloc((size_t)n_sym * Lp * 2)) return e;
+    if (int e = sym.alloc((size_t)n_sym * 2)) return e;
+    if (int e = iv.alloc((size_t)n_sym * 4)) return e;
+    L3C_CUDA(cudaMemcpy(cdf.p, cdf_host, (size_t)n_sym * Lp * 2, cudaMemcpyHostToDevice));
+    L3C_CUDA(cudaMemcpy(sym.p, sym_host, (size_t)n_sym * 2, cudaMemcpyHostToDevice));
+    table_intervals_kernel<<<(unsigned)ceil_div64(n_sym, 256), 256>>>(cdf.as<uint16_t>(), sym.as<int16_t>(),
+                                                                      n_sym, Lp, iv.as<uint32_t>());
+    L3C_LAUNCH_CHECK("table_intervals_kernel");
+    return run_encode(iv.as<uint32_t>(), n_sym, out_host, out_cap, out_len);
+}
+
+extern "C" int l3c_decode_cdf(const uint16_t *cdf_host, int64_t n_sym, int Lp, const uint8_t *in_host,
+                              size_t in_len, int16_t *sym_out_host) {
+    if (int e = check_stream_args("l3c_decode_cdf", n_sym, Lp)) return e;
+    L3C_REQUIRE(cdf_host && sym_out_host && (in_host || in_len == 0), "l3c_decode_cdf: null pointer");
+    const int L = Lp - 1;
+    const int pitch = (L <= 32) ? 32 : 256;
+    DevBuf cdf, table;
+    if (int e = cdf.alloc((size_t)n_sym * Lp * 2)) return e;
+    if (int e = table.alloc((size_t)n_sym * pitch * 2)) return e;
+    L3C_CUDA(cudaMemcpy(cdf.p, cdf_host, (size_t)n_sym * Lp * 2, cudaMemcpyHostToDevice));
+    repitch_kernel<<<(unsigned)ceil_div64(n_sym * pitch, 256), 256>>>(cdf.as<uint16_t>(), n_sym, Lp, pitch,
+                                                                      table.as<uint16_t>());
+    L3C_LAUNCH_CHECK("repitch_kernel");
+    return run_decode(table.as<uint16_t>(), pitch, n_sym, L, in_host, in_len, sym_out_host);
+}
+
+extern "C" int l3c_encode_logistic_mixture(const float *targets_dev, const float *means_dev,
+                                           const float *log_scales_dev, const float *probs_dev, int K,
+                                           int64_t n_sym, int Lp, const int16_t *sym_host,
+                                           uint8_t *out_host, size_t out_cap, size_t *out_len) {
+    if (int e = check_stream_args("l3c_encode_logistic_mixture", n_sym, Lp)) return e;
+    L3C_REQUIRE(targets_dev && means_dev && log_scales_dev && probs_dev && sym_host && out_host && out_len && K >= 1,
+                "l3c_encode_logistic_mixture: bad arguments");
+    for (int64_t i = 0; i < n_sym; ++i)
+        L3C_REQUIRE(sym_host[i] >= 0 && sym_host[i] <= Lp - 2, "l3c_encode_logistic_mixture: symbol out of range");
+    DevBuf sym, iv;
+    if (int e = sym.alloc((size_t)n_sym * 2)) return e;
+    if (int e = iv.alloc((size_t)n_sym * 4)) return e;
+    L3C_CUDA(cudaMemcpy(sym.p, sym_host, (size_t)n_sym * 2, cudaMemcpyHostToDevice));
+    plane_intervals_kernel<<<(unsigned)ceil_div64(n_sym, 128), 128>>>(
+        targets_dev, means_dev, log_scales_dev, probs_dev, K, n_sym, Lp, sym.as<int16_t>(), iv.as<uint32_t>());
+    L3C_LAUNCH_CHECK("plane_intervals_kernel");
+    return run_encode(iv.as<uint32_t>(), n_sym, out_host, out_cap, out_len);
+}
+
+extern "C" int l3c_decode_logistic_mixture(const float *targets_dev, const float *means_dev,
+                                           const float *log_scales_dev, const float *probs_dev, int K,
+                                           int64_t n_sym, int Lp, const uint8_t *in_host, size_t in_len,
+                                           int16_t *sym_out_host) {
+    if (int e = check_stream_args("l3c_decode_logistic_mixture", n_sym, Lp)) return e;
+    L3C_REQUIRE(targets_dev && means_dev && log_scales_dev && probs_dev && sym_out_host && K >= 1 &&
+                    (in_host || in_len == 0),
+                "l3c_decode_logistic_mixture: bad arguments");
+    const int L = Lp - 1;
+    const int pitch = (L <= 32) ? 32 : 256;
+    DevBuf table;
+    if (int e = table.alloc((size_t)n_sym * pitch * 2)) return e;
+    plane_table_kernel<<<(unsigned)ceil_div64(n_sym * pitch, 256), 256>>>(
+        targets_dev, means_dev, log_scales_dev, probs_dev, K, n_sym, Lp, pitch, table.as<uint16_t>());
+    L3C_LAUNCH_CHECK("plane_table_kernel");
+    return run_decode(table.as<uint16_t>(), pitch, n_sym, L, in_host, in_len, sym_out_host);
+}

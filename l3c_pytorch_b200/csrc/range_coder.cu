@@ -1,0 +1,331 @@
+// range_coder.cu -- batched binary arithmetic coder for sm_100a: one warp per stream.
+//
+// Bit-exact re-statement of the reference coder's integer arithmetic
+//   encoder: /root/reference/src/torchac/torchac_backend/torchac.cpp:152-227 (+ bit sink :63-93)
+//   decoder: /root/reference/src/torchac/torchac_backend/torchac.cpp:299-381 (+ :96-128, :276-296)
+// re-designed for the GPU:
+//   * the reference's bit-at-a-time renormalisation loops are collapsed into two count-leading-
+//     zeros steps (all "equal MSB" shifts first, then all "underflow" shifts -- the reference loop
+//     can only ever visit them in that order);
+//   * the encoder consumes pre-computed 32-bit (c_low, c_high-1) intervals (one coalesced load per
+//     32 symbols) instead of indexing a CDF table with the symbol;
+//   * the decoder replaces the per-row binary search by a warp-wide comparison of the whole CDF row
+//     against the scaled code value (no division: cdf[m]*span < (value-low+1)<<16  <=>
+//     cdf[m] <= ((value-low+1)*2^16-1)/span), followed by warp max/min/add reductions (REDUX);
+//     rows are prefetched 8 symbols ahead so HBM latency stays off the serial dependency chain;
+//   * coder state can be saved/restored so that a stream may be decoded in chunks while later CDF
+//     rows are still being built (RGB channel pipelining).
+#include "common.cuh"
+
+namespace l3c {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int ENC_WARPS_PER_CTA = 1;
+constexpr int DEC_WARPS_PER_CTA = 1;
+
+// ---------------------------------------------------------------------------------------------
+// encoder
+// ---------------------------------------------------------------------------------------------
+struct BitSink {
+    uint32_t *out;       // word pointer (big-endian words)
+    uint32_t cap_words;
+    uint32_t wpos;
+    uint64_t acc;
+    int nacc;            // < 32 between calls
+    int lane;
+
+    __device__ __forceinline__ void put(uint32_t v, int n) {   // 0 <= n <= 32, v < 2^n
+        acc = (acc << n) | v;
+        nacc += n;
+        if (nacc >= 32) {
+            const uint32_t w = (uint32_t)(acc >> (nacc - 32));
+            if (lane == 0 && wpos < cap_words) out[wpos] = __byte_perm(w, 0, 0x0123);
+            wpos++;
+            nacc -= 32;
+        }
+    }
+    __device__ __forceinline__ void put_run(uint32_t bit, uint32_t count) {
+        const uint32_t ones = bit ? 0xFFFFFFFFu : 0u;
+        while (count >= 32) {
+            put(ones, 32);
+            count -= 32;
+        }
+        if (count) put(ones & ((1u << count) - 1u), (int)count);
+    }
+};
+
+__global__ void __launch_bounds__(32 * ENC_WARPS_PER_CTA)
+ac_encode_kernel(const l3c_enc_stream_t *__restrict__ streams, int n_streams,
+                 uint32_t *__restrict__ out_len) {
+    const int sid = blockIdx.x * ENC_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (sid >= n_streams) return;
+    const int lane = threadIdx.x & 31;
+    const l3c_enc_stream_t st = streams[sid];
+    const uint32_t *__restrict__ iv = st.intervals;
+    const uint32_t n = st.n_sym;
+
+    BitSink sink;
+    sink.out = reinterpret_cast<uint32_t *>(st.out);
+    sink.cap_words = st.out_cap >> 2;
+    sink.wpos = 0;
+    sink.acc = 0;
+    sink.nacc = 0;
+    sink.lane = lane;
+
+    uint32_t low = 0u, high = 0xFFFFFFFFu, pending = 0u;
+
+    uint32_t next = (lane < n) ? __ldg(iv + lane) : 0u;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t mine = next;
+        const uint32_t nb = base + 32 + lane;
+        next = (nb < n) ? __ldg(iv + nb) : 0u;              // prefetch the next 32 intervals
+        const int cnt = (n - base < 32u) ? (int)(n - base) : 32;
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+            const uint32_t v = __shfl_sync(FULL, mine, j);
+            const uint32_t c_lo = v & 0xFFFFu;
+            const uint32_t c_hi = (v >> 16) + 1u;
+            const uint32_t r = high - low;                   // span - 1
+            // span * c  ==  r * c + c   (span may be 2^32, keep it out of 32-bit registers)
+            const uint64_t p_hi = (uint64_t)r * c_hi + c_hi;
+            const uint64_t p_lo = (uint64_t)r * c_lo + c_lo;
+            high = low - 1u + (uint32_t)(p_hi >> 16);
+            low = low + (uint32_t)(p_lo >> 16);
+
+            const int k = __clz((int)(low ^ high));          // leading bits already decided
+            if (k > 0) {
+                if (pending == 0u) {
+                    sink.put(low >> (32 - k), k);
+                } else {
+                    const uint32_t b0 = low >> 31;
+                    sink.put(b0, 1);
+                    sink.put_run(b0 ^ 1u, pending);
+                    pending = 0u;
+                    if (k > 1) sink.put((low << 1) >> (33 - k), k - 1);
+                }
+                low <<= k;
+                high = (high << k) | ((1u << k) - 1u);
+            }
+            // underflow: low = 01..., high = 10...: drop the second MSB as often as that holds
+            const uint32_t m = (low & ~high) << 1;
+            const int u = __clz((int)~m);
+            if (u > 0) {
+                pending += (uint32_t)u;
+                low = (low << u) & 0x7FFFFFFFu;
+                high = (high << u) | 0x80000000u | ((1u << u) - 1u);
+            }
+        }
+    }
+
+    // termination (torchac.cpp:209-219): one more bit + the owed underflow bits, zero-padded
+    pending += 1u;
+    const uint32_t fin = (low < 0x40000000u) ? 0u : 1u;
+    sink.put(fin, 1);
+    sink.put_run(fin ^ 1u, pending);
+    const uint32_t total = sink.wpos * 4u + (uint32_t)((sink.nacc + 7) >> 3);
+    if (sink.nacc > 0) {
+        const uint32_t w = (uint32_t)(sink.acc << (32 - sink.nacc));
+        if (lane == 0 && sink.wpos < sink.cap_words) sink.out[sink.wpos] = __byte_perm(w, 0, 0x0123);
+    }
+    if (lane == 0) out_len[sid] = total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// decoder
+// ---------------------------------------------------------------------------------------------
+struct BitSource {
+    const uint32_t *in;  // big-endian words
+    uint32_t n_words;
+    uint32_t wnext;      // index of the word held in `ahead`
+    uint32_t ahead;      // prefetched word (already byte-swapped)
+    uint64_t win;        // upcoming bits, left aligned
+    int navail;          // valid bits in win, kept >= 32
+    uint32_t consumed;   // total bits taken (saved as coder state)
+
+    __device__ __forceinline__ uint32_t word(uint32_t i) const {
+        return (i < n_words) ? __byte_perm(__ldg(in + i), 0, 0x0123) : 0u;   // zero fill past end
+    }
+    __device__ __forceinline__ void seek(uint32_t bitpos) {
+        const uint32_t w = bitpos >> 5;
+        const int off = (int)(bitpos & 31u);
+        win = (((uint64_t)word(w) << 32) | (uint64_t)word(w + 1)) << off;
+        navail = 64 - off;
+        wnext = w + 2;
+        ahead = word(wnext);
+        consumed = bitpos;
+        refill();
+    }
+    __device__ __forceinline__ void refill() {
+        if (navail < 32) {
+            win |= (uint64_t)ahead << (32 - navail);
+            navail += 32;
+            wnext++;
+            ahead = word(wnext);
+        }
+    }
+    __device__ __forceinline__ uint32_t take(int n) {        // 1 <= n <= 32
+        const uint32_t v = (uint32_t)(win >> (64 - n));
+        win <<= n;
+        navail -= n;
+        consumed += (uint32_t)n;
+        refill();
+        return v;
+    }
+};
+
+template <int EPL>
+struct RowRegs;
+template <>
+struct RowRegs<8> {
+    uint4 v;
+    __device__ __forceinline__ void load(const uint16_t *row, int lane, int /*L*/) {
+        v = __ldg(reinterpret_cast<const uint4 *>(row) + lane);
+    }
+    __device__ __forceinline__ uint32_t get(int j, int lane, int L) const {
+        const uint32_t w = (j < 2) ? v.x : (j < 4) ? v.y : (j < 6) ? v.z : v.w;
+        const uint32_t e = (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+        return (lane * 8 + j < L) ? e : 0x10000u;       // padding entries never compare true
+    }
+};
+template <>
+struct RowRegs<1> {
+    uint32_t v;
+    __device__ __forceinline__ void load(const uint16_t *row, int lane, int L) {
+        v = (lane < L) ? (uint32_t)__ldg(row + lane) : 0x10000u;
+    }
+    __device__ __forceinline__ uint32_t get(int, int, int) const { return v; }
+};
+
+template <int EPL>
+__global__ void __launch_bounds__(32 * DEC_WARPS_PER_CTA)
+ac_decode_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, int L,
+                 uint32_t first, uint32_t count) {
+    constexpr int D = 8;   // row prefetch distance (symbols)
+    const int sid = blockIdx.x * DEC_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (sid >= n_streams) return;
+    const int lane = threadIdx.x & 31;
+    const l3c_dec_stream_t st = streams[sid];
+    const uint32_t n = st.n_sym;
+    if (first >= n) return;
+    const uint32_t last = (count > n - first) ? n : first + count;   // exclusive
+
+    BitSource src;
+    src.in = reinterpret_cast<const uint32_t *>(st.in);
+    src.n_words = (st.in_len + 3u) >> 2;
+
+    uint32_t low, high, value;
+    if (first == 0) {
+        low = 0u;
+        high = 0xFFFFFFFFu;
+        src.seek(0);
+        value = src.take(32);
+    } else {
+        low = st.state[0];
+        high = st.state[1];
+        value = st.state[2];
+        src.seek(st.state[3]);
+    }
+
+    const uint16_t *__restrict__ table = st.table;
+    const int64_t pitch = st.row_pitch;
+
+    RowRegs<EPL> ring[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const uint32_t i = first + d;
+        if (i < last) ring[d].load(table + (int64_t)i * pitch, lane, L);
+    }
+
+    for (uint32_t base = first; base < last; base += D) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const uint32_t i = base + d;
+            if (i >= last) break;
+            const RowRegs<EPL> cur = ring[d];
+            if (i + D < last) ring[d].load(table + (int64_t)(i + D) * pitch, lane, L);
+
+            const uint32_t r = high - low;                              // span - 1
+            const uint64_t target = ((uint64_t)(value - low) + 1ull) << 16;
+            uint32_t lane_lo = 0u, lane_hi = 0x10000u;
+            int n_true = 0;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                const uint32_t e = cur.get(j, lane, L);
+                const uint64_t prod = (uint64_t)r * e + e;              // e * span
+                bool f = prod < target;                                 // cdf[m] <= count
+                if (j == 0 && lane == 0) f = true;                      // symbol 0 is the floor
+                lane_lo = f ? max(lane_lo, e) : lane_lo;
+                lane_hi = f ? lane_hi : min(lane_hi, e);
+                n_true += f ? 1 : 0;
+            }
+            const uint32_t c_lo = __reduce_max_sync(FULL, lane_lo);
+            const uint32_t c_hi = __reduce_min_sync(FULL, lane_hi);
+            const int sym = __reduce_add_sync(FULL, n_true) - 1;
+            if (lane == 0) st.sym_out[i] = (uint8_t)sym;
+            if (i == n - 1) break;                                      // torchac.cpp:335-337
+
+            const uint64_t p_hi = (uint64_t)r * c_hi + c_hi;
+            const uint64_t p_lo = (uint64_t)r * c_lo + c_lo;
+            high = low - 1u + (uint32_t)(p_hi >> 16);
+            low = low + (uint32_t)(p_lo >> 16);
+
+            const int k = __clz((int)(low ^ high));
+            if (k > 0) {
+                low <<= k;
+                high = (high << k) | ((1u << k) - 1u);
+                value = (value << k) | src.take(k);
+            }
+            const uint32_t m = (low & ~high) << 1;
+            const int u = __clz((int)~m);
+            if (u > 0) {
+                low = (low << u) & 0x7FFFFFFFu;
+                high = (high << u) | 0x80000000u | ((1u << u) - 1u);
+                value = ((value << u) | src.take(u)) ^ 0x80000000u;
+            }
+        }
+    }
+
+    if (lane == 0 && st.state != nullptr) {
+        st.state[0] = low;
+        st.state[1] = high;
+        st.state[2] = value;
+        st.state[3] = src.consumed;
+    }
+}
+
+}  // namespace l3c
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" int l3c_ac_encode_streams(const l3c_enc_stream_t *streams_dev, int n_streams,
+                                     uint32_t *out_len_dev, void *stream) {
+    using namespace l3c;
+    L3C_REQUIRE(n_streams >= 0, "l3c_ac_encode_streams: n_streams=%d", n_streams);
+    if (n_streams == 0) return L3C_OK;
+    L3C_REQUIRE(streams_dev && out_len_dev, "l3c_ac_encode_streams: null pointer");
+    const int grid = ceil_div(n_streams, ENC_WARPS_PER_CTA);
+    ac_encode_kernel<<<grid, 32 * ENC_WARPS_PER_CTA, 0, (cudaStream_t)stream>>>(
+        streams_dev, n_streams, out_len_dev);
+    L3C_LAUNCH_CHECK("ac_encode_kernel");
+    return L3C_OK;
+}
+
+extern "C" int l3c_ac_decode_streams(const l3c_dec_stream_t *streams_dev, int n_streams, int L,
+                                     uint32_t first, uint32_t count, void *stream) {
+    using namespace l3c;
+    L3C_REQUIRE(n_streams >= 0, "l3c_ac_decode_streams: n_streams=%d", n_streams);
+    L3C_REQUIRE(L >= 1 && L <= 256, "l3c_ac_decode_streams: L=%d not in [1,256]", L);
+    if (n_streams == 0 || count == 0) return L3C_OK;
+    L3C_REQUIRE(streams_dev, "l3c_ac_decode_streams: null pointer");
+    const int grid = ceil_div(n_streams, DEC_WARPS_PER_CTA);
+    if (L <= 32) {
+        ac_decode_kernel<1><<<grid, 32 * DEC_WARPS_PER_CTA, 0, (cudaStream_t)stream>>>(
+            streams_dev, n_streams, L, first, count);
+    } else {
+        ac_decode_kernel<8><<<grid, 32 * DEC_WARPS_PER_CTA, 0, (cudaStream_t)stream>>>(
+            streams_dev, n_streams, L, first, count);
+    }
+    L3C_LAUNCH_CHECK("ac_decode_kernel");
+    return L3C_OK;
+}

@@ -1,0 +1,36 @@
+import functools
+import itertools
+
+
+def return_list(f):
+    @functools.wraps(f)
+    def wrapper(*a, **kw):
+        return list(f(*a, **kw))
+    return wrapper
+
+
+def return_tuple(f):
+    @functools.wraps(f)
+    def wrapper(*a, **kw):
+        return tuple(f(*a, **kw))
+    return wrapper
+
+
+def unzip(it):
+    return tuple(zip(*it))
+
+
+def identity(x):
+    return x
+
+
+def lconcat(it):
+    return list(itertools.chain.from_iterable(it))
+
+
+def compose(*fs):
+    def composed(x):
+        for f in reversed(fs):
+            x = f(x)
+        return x
+    return composed
