@@ -93,7 +93,8 @@ int l3c_ac_encode_streams(const l3c_enc_stream_t *streams_dev, int n_streams,
 
 typedef struct {
     const uint16_t *table;      /* dev: CDF rows for symbols [0, n_sym) of this stream           */
-    const uint8_t *in;          /* dev: code bytes, 4-byte aligned, readable up to in_len        */
+    const uint8_t *in;          /* dev: code bytes at ANY byte address (decoded in place from the  */
+                                /*      container); the buffer must be readable 4 bytes past the end */
     uint8_t *sym_out;           /* dev: n_sym decoded symbols                                    */
     uint32_t *state;            /* dev: 4 words of coder state (low, high, value, bitpos);        */
                                 /*      lets one stream be decoded in several launches (chunks)   */
@@ -108,6 +109,16 @@ typedef struct {
 int l3c_ac_decode_streams(const l3c_dec_stream_t *streams_dev, int n_streams, int L,
                           uint32_t first, uint32_t count, void *stream);
 
+/* Copies the first len_dev[i] bytes of every encoder slot to blob_dev + dst_off_dev[i] (byte
+ * offsets: the final .l3c container layout, so ONE device->host copy returns a whole batch). */
+int l3c_pack_streams(const l3c_enc_stream_t *streams_dev, const uint32_t *len_dev,
+                     const uint64_t *dst_off_dev, int n_streams, uint8_t *blob_dev, void *stream);
+
+/* intervals_dev[i] = lut_dev[sym_dev[i]] -- coding intervals when all pixels share one CDF row
+ * (uniform prior of the coarsest scale, bitcoding.py:171-186). lut entry = c_low | (c_high-1)<<16. */
+int l3c_lut_intervals(const uint8_t *sym_dev, const uint32_t *lut_dev, int64_t n,
+                      uint32_t *intervals_dev, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * C. Discretised-logistic-mixture head
  *    (reference: criterion/logistic_mixture.py:134-275, torchac.py:174-213,
@@ -120,18 +131,18 @@ int l3c_uniform_cdf_row(int L, uint16_t *row_host);
 
 /* Per-symbol coding intervals for all C channels of one scale of a batch.
  *   l_dev      f32 NHWC [N][HW][Kp], Kp = (rgb ? 4 : 3) * C * K, channel index p*C*K + c*K + k
- *   sym_dev    uint8 [N][C][HW]  symbols being coded (also supply the RGB coupling values)
- *   values_dev f32 [L] value of each symbol (0..255 for RGB, the quantiser levels otherwise);
- *              only used for the RGB mean coupling
+ *   sym_dev    uint8 [N][C][HW]  symbols being coded (for RGB they are also the values that
+ *              enter the mean coupling, logistic_mixture.py:262-272)
  *   targets_dev f32 [L+1] bin edges (coders_helpers.py:44-46)
  *   intervals_dev uint32 [N][C][HW] out */
 int l3c_dmll_intervals(const float *l_dev, const uint8_t *sym_dev, const float *targets_dev,
                        int N, int HW, int C, int K, int L, int rgb, uint32_t *intervals_dev,
                        void *stream);
 
-/* uint16 CDF rows (pitch entries each, pitch >= L, multiple of 8) for channel c of pixels
- * [pix0, pix0+npix) of every image: table_dev[(n*HW + p) * pitch + l].  For rgb && c > 0 the
- * already decoded channels are read from sym_dev. */
+/* uint16 CDF rows (pitch = 32 for L <= 32, else 256 entries) of channel c -- or of all C channels
+ * when c < 0 (non-RGB scales: channels are conditionally independent) -- for pixels
+ * [pix0, pix0+npix) of every image: table_dev[((n*C + c)*HW + p) * pitch + l].  For rgb && c > 0
+ * the already decoded channels are read from sym_dev. */
 int l3c_dmll_build_table(const float *l_dev, const uint8_t *sym_dev, const float *targets_dev,
                          int N, int HW, int C, int K, int L, int rgb, int c, int pix0, int npix,
                          uint16_t *table_dev, int pitch, void *stream);
@@ -140,7 +151,15 @@ int l3c_dmll_build_table(const float *l_dev, const uint8_t *sym_dev, const float
  * target value of symbol s is values_dev[s] (logistic_mixture.py:146-207). */
 int l3c_dmll_nll(const float *l_dev, const uint8_t *sym_dev, const float *values_dev,
                  int N, int HW, int C, int K, int L, int rgb, float x_min, float x_max,
-                 double *nll_dev, void *stream);
+                 double *nll_dev, float *nll_map_dev /* f32 [N][C][HW] per-sub-pixel nats, or NULL */,
+                 void *stream);
+
+/* Reference-shaped per-channel mixture parameters (CDFOut, logistic_mixture.py:61-65,134-141,
+ * 248-275): softmax(pi), mu (incl. RGB coupling from x_dec_dev f32 [N][C][HW]) and clamped
+ * log sigma, each f32 [N][K][HW]. */
+int l3c_dmll_channel_params(const float *l_dev, const float *x_dec_dev, int N, int HW, int C, int K,
+                            int rgb, int c, float *pi_dev, float *mu_dev, float *log_scales_dev,
+                            void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * D. Convolution stack (reference: modules/net.py:89-184, edsr.py:52-119, head.py:26-59,

@@ -1,0 +1,65 @@
+"""MultiscaleBlueprint: API facade of the model + losses
+(/root/reference/src/blueprints/multiscale_blueprint.py:42-150), backed by the sm_100a kernels."""
+from collections import namedtuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import pad as _pad
+from .network import MultiscaleNetwork, Out
+
+MultiscaleLoss = namedtuple('MultiscaleLoss', ['loss_pc', 'nonrecursive_bpsps', 'recursive_bpsps'])
+
+DEVICE = torch.device('cuda:0')
+
+
+class MultiscaleBlueprint(nn.Module):
+    def __init__(self, config_ms, device=None):
+        super(MultiscaleBlueprint, self).__init__()
+        net = MultiscaleNetwork(config_ms)          # default init on the CPU generator, as the reference
+        self.device = torch.device(device) if device is not None else DEVICE
+        if torch.cuda.is_available():
+            net.to(self.device)
+        self.net = net
+        self.losses = net.get_losses()
+
+    def set_eval(self):
+        self.net.eval()
+        self.losses.loss_dmol_rgb.eval()
+        self.losses.loss_dmol_n.eval()
+        return self
+
+    def forward(self, in_batch, auto_recurse=0) -> Out:
+        """in_batch: NCHW 0..255 (float / long / uint8) on the GPU."""
+        return self.net(in_batch, auto_recurse)
+
+    def get_loss(self, out: Out, num_subpixels_before_pad=None) -> MultiscaleLoss:
+        """Theoretical bpsp per scale, incl. the uniform-prior final scale
+        (multiscale_blueprint.py:64-95)."""
+        costs, final_cost_uniform, num_subpixels = self.losses.get(out)
+        if num_subpixels_before_pad:
+            assert num_subpixels_before_pad <= num_subpixels, num_subpixels_before_pad
+            num_subpixels = num_subpixels_before_pad
+        conversion = np.log(2.) * num_subpixels
+        costs_bpsp = [cost / conversion for cost in costs]
+        nonrecursive_bpsps = costs_bpsp[:out.auto_recursive_from] + [final_cost_uniform / conversion]
+        return MultiscaleLoss(sum(costs_bpsp), nonrecursive_bpsps, None)
+
+    @staticmethod
+    def unpack_batch_pad(raw, fac):
+        if len(raw.shape) == 3:
+            raw = raw.unsqueeze(0)
+        assert len(raw.shape) == 4
+        raw = MultiscaleBlueprint.pad(raw, fac)
+        raw = raw.to(DEVICE)
+        return raw.float(), raw.long()
+
+    @staticmethod
+    def pad(raw, fac):
+        raw, _ = _pad.pad(raw, fac, mode=MultiscaleBlueprint.get_padding_mode())
+        return raw
+
+    @staticmethod
+    def get_padding_mode():
+        return 'constant'

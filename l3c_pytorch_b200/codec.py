@@ -1,0 +1,268 @@
+"""Batched, device-resident encode/decode of `.l3c` containers -- the B200-first core that the
+reference-shaped `Bitcoding` class (bitcoding.py) drives.
+
+What the reference does one image, one scale, one channel at a time with a GPU->CPU round trip per
+channel (/root/reference/src/bitcoding/bitcoding.py:85-123,163-294, coders.py:38-90) is done here
+for a whole batch of equally sized images with
+  * ONE network pass,
+  * one interval kernel per scale (no CDF table on the encode side),
+  * ONE range-coder launch covering every stream of every image (N * 18 warps for L3C),
+  * ONE gather kernel + ONE device->host copy producing the byte-exact container layout
+    (bitcoding.py:326-363: 4 x u16 padding | per scale: u8 C, u16 H, u16 W | per channel: u32 len +
+    stream | 4-byte magic).
+Decoding uploads the concatenated containers once and decodes every stream in place.
+"""
+import struct
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import engine as E
+from .dmll import non_shared_get_K
+
+MAGIC = b'\x46\xE2\x84\x92'          # bitcoding.py:36
+
+
+def _slot_cap(n_sym):
+    """worst case: every symbol has probability 2^-16 -> 17 bits, plus termination."""
+    return ((n_sym * 17 + 7) // 8 + 64 + 3) & ~3
+
+
+class ContainerLayout(object):
+    """Byte layout of one container given its per-stream lengths (scale order coarse -> fine)."""
+
+    def __init__(self, shapes):
+        self.shapes = shapes            # [(scale, C, H, W)] coarse -> fine
+
+    def header_and_offsets(self, lens, pad_tuple):
+        """lens: stream byte counts in container order.  Returns (total size, [(offset, bytes)]
+        header pieces, [stream offsets])."""
+        pieces = [(0, struct.pack('<4H', *pad_tuple))]
+        pos = 8
+        offs = []
+        i = 0
+        for (_, C, H, W) in self.shapes:
+            pieces.append((pos, struct.pack('<BHH', C, H, W)))
+            pos += 5
+            for _ in range(C):
+                n = int(lens[i])
+                pieces.append((pos, struct.pack('<I', n)))
+                pos += 4
+                offs.append(pos)
+                pos += n
+                i += 1
+            pieces.append((pos, MAGIC))
+            pos += 4
+        return pos, pieces, offs
+
+
+def parse_container(data):
+    """-> (pad_tuple, [(C, H, W, [(offset, length), ...])] coarse -> fine).  Raises ValueError on a
+    malformed file (the reference asserts on the magic, bitcoding.py:154)."""
+    if len(data) < 8:
+        raise ValueError('container too short')
+    pad_tuple = struct.unpack_from('<4H', data, 0)
+    pos = 8
+    scales = []
+    while pos < len(data):
+        if pos + 5 > len(data):
+            raise ValueError('truncated scale header')
+        C, H, W = struct.unpack_from('<BHH', data, pos)
+        pos += 5
+        streams = []
+        for _ in range(C):
+            if pos + 4 > len(data):
+                raise ValueError('truncated stream length')
+            n, = struct.unpack_from('<I', data, pos)
+            pos += 4
+            if pos + n > len(data):
+                raise ValueError('stream runs past the end of the file')
+            streams.append((pos, n))
+            pos += n
+        if data[pos:pos + 4] != MAGIC:
+            raise ValueError('scale separator missing: not a valid .l3c file')
+        pos += 4
+        scales.append((C, H, W, streams))
+    return pad_tuple, scales
+
+
+class BatchCodec(object):
+    def __init__(self, blueprint):
+        self.blueprint = blueprint
+        self.net = blueprint.net
+        self._const = {}
+
+    # ------------------------------------------------------------------------------------------
+    def iter_scale_dmll(self):
+        """coarse -> fine: (scale, dmll, uniform) -- bitcoding.py:163-169."""
+        losses = self.blueprint.losses
+        for scale in reversed(range(self.net.scales + 1)):
+            yield (scale, losses.loss_dmol_rgb if scale == 0 else losses.loss_dmol_n,
+                   scale == self.net.scales)
+
+    def _uniform(self, L, device):
+        key = ('uniform', L, str(device))
+        if key not in self._const:
+            row = E.uniform_cdf_row(L).astype(np.int64)
+            hi = np.concatenate([row[1:L], [65536]])
+            lut = np.zeros(256, np.int64)
+            lut[:L] = row[:L] | ((hi - 1) << 16)
+            lut_dev = torch.from_numpy(lut.astype(np.uint32).view(np.int32).copy()).to(device)
+            pitch = E.table_pitch(L)
+            trow = np.zeros(pitch, np.uint16)
+            trow[:L] = row[:L]
+            row_dev = torch.from_numpy(trow.view(np.int16).copy()).to(device)
+            self._const[key] = (lut_dev, row_dev)
+        return self._const[key]
+
+    def _rgb_shift(self, device):
+        """RGB baselines feed `S - 255*rgb_mean` to the decoder nets (net.py:77-80; SURVEY finding 2)."""
+        if not self.net._rgb:
+            return None
+        return self.net.nets[0].enc._consts(device)[1]
+
+    # ------------------------------------------------------------------------------------------
+    def encode_batch(self, imgs_u8, pad_tuple=(0, 0, 0, 0), out=None, to_host=True):
+        """imgs_u8: uint8 [N,3,H,W] on the GPU, H and W multiples of 2**num_scales.
+        Returns a list of N container byte strings (or, with to_host=False, the device blob,
+        per-image sizes and offsets, leaving the bytes in HBM).  `out`: a precomputed network Out."""
+        assert imgs_u8.dtype == torch.uint8 and imgs_u8.dim() == 4 and imgs_u8.shape[1] == 3
+        dev = imgs_u8.device
+        N = imgs_u8.shape[0]
+        if out is None:
+            out = self.net(imgs_u8)
+        K = self.net.config_ms.prob.K
+
+        # ---- per-symbol intervals, scale by scale (coarse -> fine = container order)
+        ivs, shapes = [], []
+        for scale, dmll, uniform in self.iter_scale_dmll():
+            S = out.S_u8[scale]
+            _, C, H, W = S.shape
+            shapes.append((scale, C, H, W))
+            if uniform:
+                ivs.append(E.lut_intervals(S, self._uniform(dmll.L, dev)[0]))
+            else:
+                l = out.P_nhwc[scale]
+                assert non_shared_get_K(l.shape[-1], C) == K
+                ivs.append(E.dmll_intervals(l, S, dmll.targets(dev), C, K, dmll.L, dmll.rgb_scale))
+
+        # ---- one range-coder launch for all streams; descriptor order = (image, scale, channel)
+        per_img = sum(C for (_, C, _, _) in shapes)
+        caps = np.array([_slot_cap(H * W) for (_, C, H, W) in shapes for _ in range(C)], np.int64)
+        slot_off = np.concatenate([[0], np.cumsum(caps)])
+        img_slot_bytes = int(slot_off[-1])
+        slots = torch.empty(N * img_slot_bytes, dtype=torch.uint8, device=dev)
+        desc = np.zeros(N * per_img, dtype=_lib.ENC_STREAM_DTYPE)
+        d = desc.reshape(N, per_img)
+        j = 0
+        for iv, (_, C, H, W) in zip(ivs, shapes):
+            base = iv.data_ptr()
+            for c in range(C):
+                d['intervals'][:, j] = base + (np.arange(N, dtype=np.int64) * C + c) * (H * W * 4)
+                d['n_sym'][:, j] = H * W
+                d['out_cap'][:, j] = caps[j]
+                d['out'][:, j] = slots.data_ptr() + np.arange(N, dtype=np.int64) * img_slot_bytes + slot_off[j]
+                j += 1
+        desc_dev, lens_dev = E.ac_encode_streams(desc, dev)
+        lens = lens_dev.cpu().numpy().astype(np.int64).reshape(N, per_img)       # sync #1 (tiny)
+        if (lens > caps[None, :]).any():
+            raise RuntimeError('range coder output exceeded its slot (corrupt CDF?)')
+
+        # ---- container layout + gather + single D2H
+        layout = ContainerLayout(shapes)
+        sizes, pieces_all, dst = [], [], np.zeros((N, per_img), np.int64)
+        pos = 0
+        starts = []
+        for n in range(N):
+            total, pieces, offs = layout.header_and_offsets(lens[n], pad_tuple)
+            starts.append(pos)
+            dst[n] = pos + np.asarray(offs, np.int64)
+            pieces_all.append(pieces)
+            sizes.append(total)
+            pos += (total + 15) & ~15
+        blob = torch.empty(pos + 16, dtype=torch.uint8, device=dev)
+        E.pack_streams(desc_dev, lens_dev, dst.reshape(-1), N * per_img, blob)
+        info = dict(sizes=sizes, starts=starts, lens=lens, shapes=shapes, out=out)
+        if not to_host:
+            return blob, info
+        host = torch.empty(blob.shape, dtype=torch.uint8, pin_memory=True)
+        host.copy_(blob, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                                 # sync #2
+        buf = host.numpy()
+        datas = []
+        for n in range(N):
+            s0 = starts[n]
+            for (o, b) in pieces_all[n]:
+                buf[s0 + o:s0 + o + len(b)] = np.frombuffer(b, np.uint8)
+            datas.append(buf[s0:s0 + sizes[n]].tobytes())
+        return datas, info
+
+    # ------------------------------------------------------------------------------------------
+    def decode_batch(self, datas, to_host=True):
+        """datas: list of container byte strings of equally shaped images.
+        Returns (uint8 [N,3,H,W] incl. padding, pad_tuple list)."""
+        dev = self.blueprint.device
+        N = len(datas)
+        parsed = [parse_container(d) for d in datas]
+        ref_shapes = [(C, H, W) for (C, H, W, _) in parsed[0][1]]
+        for p in parsed:
+            if [(C, H, W) for (C, H, W, _) in p[1]] != ref_shapes:
+                raise ValueError('decode_batch needs containers of identical shape')
+        if len(ref_shapes) != self.net.scales + 1:
+            raise ValueError('container has %d scales, model expects %d' % (len(ref_shapes), self.net.scales + 1))
+        # one upload of everything
+        starts = np.zeros(N, np.int64)
+        pos = 0
+        for n, dta in enumerate(datas):
+            starts[n] = pos
+            pos += (len(dta) + 15) & ~15
+        host = torch.zeros(pos + 16, dtype=torch.uint8, pin_memory=True)
+        hb = host.numpy()
+        for n, dta in enumerate(datas):
+            hb[starts[n]:starts[n] + len(dta)] = np.frombuffer(dta, np.uint8)
+        blob = host.to(dev, non_blocking=True)
+        K = self.net.config_ms.prob.K
+
+        bn8, F_prev, S = None, None, None
+        for idx, (scale, dmll, uniform) in enumerate(self.iter_scale_dmll()):
+            C, H, W = ref_shapes[idx]
+            HW = H * W
+            S = torch.empty(N, C, H, W, dtype=torch.uint8, device=dev)
+            desc = np.zeros(N * C, dtype=_lib.DEC_STREAM_DTYPE)
+            d = desc.reshape(N, C)
+            for n in range(N):
+                for c in range(C):
+                    off, ln = parsed[n][1][idx][3][c]
+                    d['in'][n, c] = blob.data_ptr() + starts[n] + off
+                    d['in_len'][n, c] = ln
+            d['n_sym'][:] = HW
+            d['sym_out'][:] = S.data_ptr() + (np.arange(N)[:, None] * C + np.arange(C)[None, :]) * HW
+            pitch = E.table_pitch(dmll.L)
+            if uniform:
+                row_dev = self._uniform(dmll.L, dev)[1]
+                d['table'][:] = row_dev.data_ptr()
+                d['row_pitch'][:] = 0
+                E.ac_decode_streams(desc, dev, dmll.L)
+            else:
+                l, F_prev = self.net.get_P_nhwc(scale, bn8, F_prev if self.net._fuse_feat else None)
+                table = torch.empty(N * C * HW * pitch, dtype=torch.int16, device=dev)
+                d['table'][:] = table.data_ptr() + \
+                    (np.arange(N)[:, None] * C + np.arange(C)[None, :]) * (HW * pitch * 2)
+                d['row_pitch'][:] = pitch
+                tg = dmll.targets(dev)
+                if dmll.rgb_scale:
+                    # channel c's means depend on the decoded channels < c at the same pixel
+                    # (logistic_mixture.py:262-272): build rows, then decode, channel by channel
+                    for c in range(C):
+                        E.dmll_build_table(l, S, tg, C, K, dmll.L, True, c, table)
+                        E.ac_decode_streams(np.ascontiguousarray(d[:, c]), dev, dmll.L)
+                else:
+                    E.dmll_build_table(l, S, tg, C, K, dmll.L, False, -1, table)
+                    E.ac_decode_streams(desc, dev, dmll.L)
+            if scale > 0:
+                bn8 = E.symbols_to_values(S, dmll.values(dev), self._rgb_shift(dev))
+        pads = [p[0] for p in parsed]
+        if to_host:
+            return S.cpu(), pads
+        return S, pads

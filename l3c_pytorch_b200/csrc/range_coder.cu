@@ -134,16 +134,33 @@ ac_encode_kernel(const l3c_enc_stream_t *__restrict__ streams, int n_streams,
 // decoder
 // ---------------------------------------------------------------------------------------------
 struct BitSource {
-    const uint32_t *in;  // big-endian words
-    uint32_t n_words;
-    uint32_t wnext;      // index of the word held in `ahead`
-    uint32_t ahead;      // prefetched word (already byte-swapped)
-    uint64_t win;        // upcoming bits, left aligned
-    int navail;          // valid bits in win, kept >= 32
-    uint32_t consumed;   // total bits taken (saved as coder state)
+    const uint32_t *base;  // 4-byte aligned address at or below the first code byte
+    uint32_t mis;          // stream start = (const uint8_t*)base + mis, mis in [0,3]
+    uint32_t in_len;       // bytes; everything past it reads as zero (torchac.cpp:109-112)
+    uint32_t wnext;        // index of the word held in `ahead`
+    uint32_t ahead;        // prefetched word (already big-endian -> native)
+    uint64_t win;          // upcoming bits, left aligned
+    int navail;            // valid bits in win, kept >= 32
+    uint32_t consumed;     // total bits taken (saved as coder state)
 
+    __device__ __forceinline__ void open(const uint8_t *in, uint32_t len) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(in);
+        mis = (uint32_t)(a & 3u);
+        base = reinterpret_cast<const uint32_t *>(a - mis);
+        in_len = len;
+    }
+    // 32 code bits starting at byte 4*i of the stream, MSB first; streams may start at any byte
+    // address (they are decoded in place from the container), so two aligned words are funnelled.
     __device__ __forceinline__ uint32_t word(uint32_t i) const {
-        return (i < n_words) ? __byte_perm(__ldg(in + i), 0, 0x0123) : 0u;   // zero fill past end
+        const uint32_t b = 4u * i;
+        if (b >= in_len) return 0u;
+        const uint32_t a0 = __ldg(base + i);
+        const uint32_t a1 = (mis != 0u) ? __ldg(base + i + 1) : 0u;
+        const uint32_t raw = __funnelshift_r(a0, a1, 8u * mis);      // little-endian bytes b..b+3
+        uint32_t w = __byte_perm(raw, 0, 0x0123);
+        const uint32_t rem = in_len - b;
+        if (rem < 4u) w &= 0xFFFFFFFFu << (8u * (4u - rem));
+        return w;
     }
     __device__ __forceinline__ void seek(uint32_t bitpos) {
         const uint32_t w = bitpos >> 5;
@@ -210,8 +227,7 @@ ac_decode_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, in
     const uint32_t last = (count > n - first) ? n : first + count;   // exclusive
 
     BitSource src;
-    src.in = reinterpret_cast<const uint32_t *>(st.in);
-    src.n_words = (st.in_len + 3u) >> 2;
+    src.open(st.in, st.in_len);
 
     uint32_t low, high, value;
     if (first == 0) {
@@ -293,6 +309,29 @@ ac_decode_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// gather the variable-length code streams into one contiguous blob (container layout, byte offsets)
+// ---------------------------------------------------------------------------------------------
+constexpr int PACK_CHUNK = 16384;
+__global__ void pack_streams_kernel(const l3c_enc_stream_t *__restrict__ streams,
+                                    const uint32_t *__restrict__ lens,
+                                    const uint64_t *__restrict__ dst_off, uint8_t *__restrict__ blob) {
+    const l3c_enc_stream_t st = streams[blockIdx.y];
+    const uint32_t len = min(lens[blockIdx.y], st.out_cap);
+    const uint32_t b0 = blockIdx.x * PACK_CHUNK;
+    if (b0 >= len) return;
+    const uint32_t b1 = min(b0 + PACK_CHUNK, len);
+    uint8_t *dst = blob + dst_off[blockIdx.y];
+    for (uint32_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) dst[i] = st.out[i];
+}
+
+// intervals from a shared 256-entry LUT (uniform prior: every pixel has the same CDF row)
+__global__ void lut_intervals_kernel(const uint8_t *__restrict__ sym, const uint32_t *__restrict__ lut,
+                                     int64_t n, uint32_t *__restrict__ iv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) iv[i] = __ldg(lut + sym[i]);
+}
+
 }  // namespace l3c
 
 // ---------------------------------------------------------------------------------------------
@@ -327,5 +366,31 @@ extern "C" int l3c_ac_decode_streams(const l3c_dec_stream_t *streams_dev, int n_
             streams_dev, n_streams, L, first, count);
     }
     L3C_LAUNCH_CHECK("ac_decode_kernel");
+    return L3C_OK;
+}
+
+extern "C" int l3c_pack_streams(const l3c_enc_stream_t *streams_dev, const uint32_t *len_dev,
+                                const uint64_t *dst_off_dev, int n_streams, uint8_t *blob_dev,
+                                void *stream) {
+    using namespace l3c;
+    if (n_streams == 0) return L3C_OK;
+    L3C_REQUIRE(streams_dev && len_dev && dst_off_dev && blob_dev && n_streams > 0 && n_streams <= 65535,
+                "l3c_pack_streams: bad arguments");
+    // grid.x covers the largest possible slot (2^22 bytes = 256 chunks is ample for 2^21 symbols);
+    // CTAs beyond a stream's length exit immediately
+    dim3 grid(256, n_streams);
+    pack_streams_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(streams_dev, len_dev, dst_off_dev, blob_dev);
+    L3C_LAUNCH_CHECK("pack_streams_kernel");
+    return L3C_OK;
+}
+
+extern "C" int l3c_lut_intervals(const uint8_t *sym_dev, const uint32_t *lut_dev, int64_t n,
+                                 uint32_t *intervals_dev, void *stream) {
+    using namespace l3c;
+    L3C_REQUIRE(sym_dev && lut_dev && intervals_dev && n >= 0, "l3c_lut_intervals: bad arguments");
+    if (n == 0) return L3C_OK;
+    lut_intervals_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(sym_dev, lut_dev, n,
+                                                                                       intervals_dev);
+    L3C_LAUNCH_CHECK("lut_intervals_kernel");
     return L3C_OK;
 }

@@ -1,0 +1,248 @@
+"""Thin Python wrappers over the C ABI: PyTorch tensors are only the *containers* (device memory,
+streams); every computation on the hot path is a kernel of libl3c_b200.so.
+
+Activation convention inside the package: NHWC fp32 contiguous tensors `[N, H, W, pitch]`.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, ConvDesc
+
+_PRECISION = {'mode': _lib.PREC_FP32}
+
+
+def set_conv_precision(name):
+    """'fp32' (CUDA-core FFMA, bit-faithful), 'tf32x3', 'tf32', 'bf16' (tcgen05 tensor cores)."""
+    _PRECISION['mode'] = _lib.PRECISIONS[name]
+
+
+def get_conv_precision():
+    return {v: k for k, v in _lib.PRECISIONS.items()}[_PRECISION['mode']]
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise ValueError('%s must be a CUDA tensor (l3c_pytorch_b200 has no CPU path)' % name)
+
+
+# ----------------------------------------------------------------------------------------------
+# weights
+# ----------------------------------------------------------------------------------------------
+class PackedConv(object):
+    """Device-side repack of one nn.Conv2d: OIHW -> [KH][KW][Cin][cout_pad] (+ padded bias).
+    Re-packed automatically when the parameter is modified (load_state_dict, .to())."""
+
+    def __init__(self, conv):
+        self.conv = conv
+        self._key = None
+        self.w = self.b = None
+
+    def get(self):
+        w, b = self.conv.weight, self.conv.bias
+        key = (w.data_ptr(), w._version, b.data_ptr(), b._version, str(w.device))
+        if key != self._key:
+            require_cuda(w, 'conv weight')
+            cout, cin, kh, kw = w.shape
+            cout_pad = (cout + 63) // 64 * 64
+            wp = torch.zeros(kh, kw, cin, cout_pad, dtype=torch.float32, device=w.device)
+            wp[..., :cout] = w.detach().float().permute(2, 3, 1, 0)
+            bp = torch.zeros(cout_pad, dtype=torch.float32, device=w.device)
+            bp[:cout] = b.detach().float()
+            self.w, self.b, self._key = wp, bp, key
+        return self.w, self.b
+
+
+def packed(conv):
+    pc = conv.__dict__.get('_l3c_packed')
+    if pc is None:
+        pc = PackedConv(conv)
+        conv.__dict__['_l3c_packed'] = pc
+    return pc.get()
+
+
+# ----------------------------------------------------------------------------------------------
+# conv stack
+# ----------------------------------------------------------------------------------------------
+def conv2d(conv, x, cin=None, relu=False, residual=None, pixel_shuffle=False, out=None, out_coff=0,
+           precision=None):
+    """y = conv(x) [+ReLU] [+residual] on NHWC tensors, parameters taken from the nn.Conv2d `conv`
+    (never called as a torch op).  `out`/`out_coff` write a channel slice of a wider NHWC buffer
+    (used for the atrous concat, prob_clf.py:71)."""
+    require_cuda(x, 'x')
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    w, b = packed(conv)
+    N, H, W, xp = x.shape
+    kh = conv.kernel_size[0]
+    stride, dil = conv.stride[0], conv.dilation[0]
+    cin = conv.in_channels if cin is None else cin
+    cout = conv.out_channels
+    pad = kh // 2 if dil == 1 else dil
+    Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    flags = (_lib.CONV_RELU if relu else 0) | (_lib.CONV_PIXEL_SHUFFLE2 if pixel_shuffle else 0)
+    if out is None:
+        if pixel_shuffle:
+            out = torch.empty(N, Ho * 2, Wo * 2, cout // 4, dtype=torch.float32, device=x.device)
+        else:
+            out = torch.empty(N, Ho, Wo, cout, dtype=torch.float32, device=x.device)
+    d = ConvDesc(x=x.data_ptr(), w=w.data_ptr(), bias=b.data_ptr(),
+                 residual=residual.data_ptr() if residual is not None else None, y=out.data_ptr(),
+                 N=N, H=H, W=W, Cin=cin, x_pitch=xp, Cout=cout, cout_pad=w.shape[-1],
+                 y_pitch=out.shape[-1], y_coff=out_coff, ksize=kh, stride=stride, dilation=dil,
+                 flags=flags, precision=_PRECISION['mode'] if precision is None else precision)
+    if residual is not None:
+        assert residual.shape == out.shape and residual.is_contiguous()
+    check(lib.l3c_conv2d(ctypes.byref(d), _stream_ptr()))
+    return out
+
+
+def rgb_prep(img_u8, conv1, conv2):
+    """uint8 planes [N,3,H,W] -> (x_sub NHWC [N,H,W,3] or None, t NHWC [N,H,W,4]); the two 1x1
+    MeanShift convs are applied as per-pixel 3x3 affines (parameters read from the modules)."""
+    require_cuda(img_u8, 'img')
+    assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous()
+    N, _, H, W = img_u8.shape
+    A1 = conv1.weight.detach().float().reshape(9).contiguous()
+    b1 = conv1.bias.detach().float().contiguous()
+    t = None
+    A2 = b2 = None
+    xsub = None
+    if conv2 is not None:
+        A2 = conv2.weight.detach().float().reshape(9).contiguous()
+        b2 = conv2.bias.detach().float().contiguous()
+        t = torch.empty(N, H, W, 4, dtype=torch.float32, device=img_u8.device)
+    else:
+        xsub = torch.empty(N, H, W, 3, dtype=torch.float32, device=img_u8.device)
+    check(lib.l3c_rgb_prep(_ptr(img_u8), _ptr(A1), _ptr(b1), _ptr(A2), _ptr(b2), N, H * W,
+                           _ptr(xsub), _ptr(t), _stream_ptr()))
+    return xsub, t
+
+
+def quantize_head(f, to_q_conv, levels):
+    """F NHWC [N,H,W,Cf] -> (sym uint8 planes [N,C,H,W], bn_q NHWC [N,H,W,8] zero padded)."""
+    N, H, W, Cf = f.shape
+    C = to_q_conv.out_channels
+    w = to_q_conv.weight.detach().float().reshape(C, Cf).t().contiguous()
+    b = to_q_conv.bias.detach().float().contiguous()
+    lev = levels.detach().float().contiguous()
+    sym = torch.empty(N, C, H, W, dtype=torch.uint8, device=f.device)
+    bnq = torch.empty(N, H, W, 8, dtype=torch.float32, device=f.device)
+    check(lib.l3c_quantize_head(_ptr(f), _ptr(w), _ptr(b), _ptr(lev), N, H * W, Cf, C, lev.numel(),
+                                _ptr(sym), _ptr(bnq), _stream_ptr()))
+    return sym, bnq
+
+
+def symbols_to_values(sym, values, shift=None):
+    """uint8 planes [N,C,H,W] -> NHWC [N,H,W,8] of values[sym] - shift (zero padded)."""
+    N, C, H, W = sym.shape
+    out = torch.empty(N, H, W, 8, dtype=torch.float32, device=sym.device)
+    check(lib.l3c_symbols_to_values(_ptr(sym), _ptr(values), _ptr(shift), N, H * W, C, values.numel(),
+                                    _ptr(out), _stream_ptr()))
+    return out
+
+
+def bicubic_half(img_u8):
+    N, C, H, W = img_u8.shape
+    assert C == 3 and img_u8.dtype == torch.uint8 and img_u8.is_contiguous()
+    out = torch.empty(N, 3, int(H * 0.5), int(W * 0.5), dtype=torch.uint8, device=img_u8.device)
+    check(lib.l3c_bicubic_half_u8(_ptr(img_u8), N, H, W, _ptr(out), _stream_ptr()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# DMLL head
+# ----------------------------------------------------------------------------------------------
+def uniform_cdf_row(L):
+    row = np.zeros(L + 1, np.uint16)
+    check(lib.l3c_uniform_cdf_row(L, row.ctypes.data_as(ctypes.c_void_p)))
+    return row
+
+
+def dmll_intervals(l, sym, targets, C, K, L, rgb):
+    """l NHWC [N,H,W,Kp]; sym uint8 [N,C,H,W] -> intervals uint32 (stored int32) [N,C,H*W]."""
+    N, H, W, _ = l.shape
+    iv = torch.empty(N, C, H * W, dtype=torch.int32, device=l.device)
+    check(lib.l3c_dmll_intervals(_ptr(l), _ptr(sym), _ptr(targets), N, H * W, C, K, L, int(rgb),
+                                 _ptr(iv), _stream_ptr()))
+    return iv
+
+
+def lut_intervals(sym, lut):
+    iv = torch.empty(sym.shape[0], sym.shape[1], sym.shape[2] * sym.shape[3], dtype=torch.int32,
+                     device=sym.device)
+    check(lib.l3c_lut_intervals(_ptr(sym), _ptr(lut), sym.numel(), _ptr(iv), _stream_ptr()))
+    return iv
+
+
+def table_pitch(L):
+    return 32 if L <= 32 else 256
+
+
+def dmll_build_table(l, sym, targets, C, K, L, rgb, c, table, pix0=0, npix=None):
+    N, H, W, _ = l.shape
+    npix = H * W - pix0 if npix is None else npix
+    check(lib.l3c_dmll_build_table(_ptr(l), _ptr(sym), _ptr(targets), N, H * W, C, K, L, int(rgb), c,
+                                   pix0, npix, _ptr(table), table_pitch(L), _stream_ptr()))
+
+
+def dmll_nll(l, sym, values, C, K, L, rgb, x_min, x_max, want_map=False):
+    """-> (per-image nats float64 [N], per-sub-pixel nats f32 [N,C,H,W] or None)."""
+    N, H, W, _ = l.shape
+    out = torch.empty(N, dtype=torch.float64, device=l.device)
+    nmap = torch.empty(N, C, H, W, dtype=torch.float32, device=l.device) if want_map else None
+    check(lib.l3c_dmll_nll(_ptr(l), _ptr(sym), _ptr(values), N, H * W, C, K, L, int(rgb),
+                           float(x_min), float(x_max), _ptr(out), _ptr(nmap), _stream_ptr()))
+    return out, nmap
+
+
+def dmll_channel_params(l, x_dec, C, K, rgb, c):
+    """l NHWC; x_dec f32 [N,C,H,W] contiguous (values of already coded channels) or None.
+    -> (softmax pi, mu, log sigma), each [N,K,H,W] f32."""
+    N, H, W, _ = l.shape
+    outs = [torch.empty(N, K, H, W, dtype=torch.float32, device=l.device) for _ in range(3)]
+    check(lib.l3c_dmll_channel_params(_ptr(l), _ptr(x_dec), N, H * W, C, K, int(rgb), c,
+                                      _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _stream_ptr()))
+    return outs
+
+
+# ----------------------------------------------------------------------------------------------
+# range coder
+# ----------------------------------------------------------------------------------------------
+def _desc_to_device(arr, device):
+    t = torch.from_numpy(arr.view(np.uint8).reshape(-1))
+    return t.to(device, non_blocking=False)
+
+
+def ac_encode_streams(desc_np, device):
+    """desc_np: numpy structured array (ENC_STREAM_DTYPE). Returns (desc_dev, lens_dev int32)."""
+    n = desc_np.shape[0]
+    desc = _desc_to_device(desc_np, device)
+    lens = torch.empty(n, dtype=torch.int32, device=device)
+    check(lib.l3c_ac_encode_streams(_ptr(desc), n, _ptr(lens), _stream_ptr()))
+    return desc, lens
+
+
+def pack_streams(desc_dev, lens_dev, dst_off_np, n, blob):
+    off = torch.from_numpy(dst_off_np.astype(np.int64)).to(blob.device)
+    check(lib.l3c_pack_streams(_ptr(desc_dev), _ptr(lens_dev), _ptr(off), n, _ptr(blob), _stream_ptr()))
+
+
+def ac_decode_streams(desc_np, device, L, first=0, count=None, desc_dev=None):
+    n = desc_np.shape[0]
+    if desc_dev is None:
+        desc_dev = _desc_to_device(desc_np, device)
+    if count is None:
+        count = int(desc_np['n_sym'].max()) if n else 0
+    check(lib.l3c_ac_decode_streams(_ptr(desc_dev), n, L, first, count, _stream_ptr()))
+    return desc_dev

@@ -1,0 +1,137 @@
+"""GPU: every conv-stack kernel against a plain PyTorch fp32 CPU reference of the same op
+(floating point: rtol 2e-5 / atol 2e-5 for the fp32 FFMA path -- only the accumulation order
+differs from MKL-DNN)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 2e-5, 2e-5
+
+
+def _conv_module(cin, cout, k, stride=1, rate=1, seed=0):
+    from l3c_pytorch_b200.network import default_conv
+    torch.manual_seed(seed)
+    return default_conv(cin, cout, k, rate=rate, stride=stride)
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().cuda()
+
+
+@pytest.mark.parametrize('cin,cout,k,stride,rate,H,W', [
+    (64, 64, 3, 1, 1, 16, 16), (64, 64, 3, 1, 1, 19, 37), (64, 64, 3, 1, 2, 24, 40), (64, 64, 3, 1, 4, 20, 33),
+    (64, 64, 5, 2, 1, 32, 48), (64, 64, 5, 2, 1, 18, 22), (64, 256, 3, 1, 1, 12, 20), (192, 120, 1, 1, 1, 9, 31),
+    (192, 150, 1, 1, 1, 16, 16), (64, 64, 3, 1, 1, 8, 16)])
+def test_conv_vs_torch(cin, cout, k, stride, rate, H, W):
+    from l3c_pytorch_b200 import engine as E
+    conv = _conv_module(cin, cout, k, stride, rate)
+    x = torch.randn(2, cin, H, W)
+    want = conv(x).detach()
+    got = E.conv2d(conv.cuda(), _nhwc(x)).cpu().permute(0, 3, 1, 2)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=RTOL, atol=ATOL)
+
+
+def test_conv_epilogues():
+    from l3c_pytorch_b200 import engine as E
+    conv = _conv_module(64, 64, 3)
+    x, r = torch.randn(2, 64, 20, 28), torch.randn(2, 64, 20, 28)
+    cc = conv.cuda()
+    got = E.conv2d(cc, _nhwc(x), relu=True).cpu().permute(0, 3, 1, 2)
+    np.testing.assert_allclose(got.numpy(), F.relu(conv.cpu()(x)).detach().numpy(), rtol=RTOL, atol=ATOL)
+    got = E.conv2d(cc.cuda(), _nhwc(x), residual=_nhwc(r)).cpu().permute(0, 3, 1, 2)
+    np.testing.assert_allclose(got.numpy(), (conv.cpu()(x) + r).detach().numpy(), rtol=RTOL, atol=ATOL)
+    # channel-slice output (atrous concat)
+    buf = torch.zeros(2, 20, 28, 192).cuda()
+    E.conv2d(conv.cuda(), _nhwc(x), out=buf, out_coff=64)
+    b = buf.cpu()
+    assert (b[..., :64] == 0).all() and (b[..., 128:] == 0).all()
+    np.testing.assert_allclose(b[..., 64:128].permute(0, 3, 1, 2).numpy(), conv.cpu()(x).detach().numpy(),
+                               rtol=RTOL, atol=ATOL)
+    # pixel shuffle
+    up = _conv_module(64, 256, 3, seed=3)
+    want = F.pixel_shuffle(up(x), 2).detach()
+    got = E.conv2d(up.cuda(), _nhwc(x), pixel_shuffle=True).cpu().permute(0, 3, 1, 2)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=RTOL, atol=ATOL)
+
+
+def test_small_channel_convs_and_padding_lanes():
+    """RGB head (Cin=3 in a pitch-4 buffer) and decoder head (Cin=5 in a pitch-8 buffer)."""
+    from l3c_pytorch_b200 import engine as E
+    head = _conv_module(3, 64, 3, seed=1)
+    x = torch.randn(1, 3, 17, 23)
+    x4 = torch.zeros(1, 17, 23, 4)
+    x4[..., :3] = x.permute(0, 2, 3, 1)
+    got = E.conv2d(head.cuda(), x4.cuda(), cin=3).cpu().permute(0, 3, 1, 2)
+    np.testing.assert_allclose(got.numpy(), head.cpu()(x).detach().numpy(), rtol=RTOL, atol=ATOL)
+    dh = _conv_module(5, 64, 1, seed=2)
+    b = torch.randn(2, 5, 9, 11)
+    b8 = torch.zeros(2, 9, 11, 8)
+    b8[..., :5] = b.permute(0, 2, 3, 1)
+    fuse = torch.randn(2, 64, 9, 11)
+    got = E.conv2d(dh.cuda(), b8.cuda(), residual=_nhwc(fuse)).cpu().permute(0, 3, 1, 2)
+    np.testing.assert_allclose(got.numpy(), (dh.cpu()(b) + fuse).detach().numpy(), rtol=RTOL, atol=ATOL)
+
+
+def test_conv_independent_of_batch_and_position():
+    """enc/dec bit-exactness: the same pixel neighbourhood gives the same bits whatever the batch
+    size, image size or tile it lands in."""
+    from l3c_pytorch_b200 import engine as E
+    conv = _conv_module(64, 64, 3).cuda()
+    x = torch.randn(3, 64, 40, 56)
+    full = E.conv2d(conv, _nhwc(x)).cpu()
+    one = E.conv2d(conv, _nhwc(x[1:2])).cpu()
+    assert torch.equal(full[1:2], one)
+    crop = E.conv2d(conv, _nhwc(x[:, :, 8:32, 16:48])).cpu()
+    assert torch.equal(full[:, 9:31, 17:47], crop[:, 1:-1, 1:-1])
+
+
+def test_rgb_prep_and_quantize_head():
+    from l3c_pytorch_b200 import engine as E
+    from oracle import model as om
+    bp = util.blueprint('cr')
+    sd = util.cpu_state_dict(bp)
+    img = torch.stack([util.make_image(i, 24, 40) for i in range(2)])
+    _, t = E.rgb_prep(img.cuda(), bp.net.sub_rgb_mean, bp.net.heads[0].head[0])
+    want = om._conv(sd, 'heads.0.head.0', om._conv(sd, 'sub_rgb_mean', img.float()))
+    np.testing.assert_allclose(t.cpu()[..., :3].permute(0, 3, 1, 2).numpy(), want.numpy(), rtol=1e-6, atol=1e-6)
+    assert (t.cpu()[..., 3] == 0).all()
+    # to_q + quantiser
+    enc = bp.net.nets[0].enc
+    Fm = torch.randn(2, 64, 10, 14) * 0.5
+    sym, bnq = E.quantize_head(_nhwc(Fm), enc.to_q[0], enc.levels)
+    q_in = om._conv(sd, 'nets.0.enc.to_q.0', Fm)
+    S, hard = om.quantize(q_in, sd['nets.0.enc.levels'])
+    s_got = sym.cpu().long()
+    flips = (s_got != S)
+    # a flip is only legitimate when q_in sits on a decision boundary to within float noise
+    if flips.any():
+        lev = sd['nets.0.enc.levels']
+        d = (q_in.unsqueeze(-1) - lev).abs().sort(-1)[0]
+        assert ((d[..., 1] - d[..., 0])[flips] < 1e-5).all()
+    assert flips.float().mean() < 1e-3
+    lev = sd['nets.0.enc.levels']
+    assert torch.equal(bnq.cpu()[..., :5].permute(0, 3, 1, 2), lev[s_got])     # exactly levels[S]
+    assert (bnq.cpu()[..., 5:] == 0).all()
+    back = E.symbols_to_values(sym, enc.levels.detach())
+    assert torch.equal(back.cpu(), bnq.cpu())                                   # decoder side == encoder side
+
+
+def test_bicubic_matches_pillow():
+    from PIL import Image
+    from l3c_pytorch_b200 import engine as E
+    for (H, W) in [(64, 64), (50, 38), (256, 256), (33, 17)]:
+        img = torch.stack([util.make_image(i, H, W) for i in range(2)])
+        # smooth one of them so that the test is not only noise
+        img[1] = torch.from_numpy(np.clip(np.cumsum(np.cumsum(img[1].numpy().astype(np.int32) - 127, 1), 2) // 40 + 128,
+                                          0, 255).astype(np.uint8))
+        got = E.bicubic_half(img.cuda()).cpu()
+        for n in range(2):
+            pil = Image.fromarray(img[n].permute(1, 2, 0).numpy())
+            w, h = pil.size
+            want = torch.from_numpy(np.array(pil.resize((int(w * 0.5), int(h * 0.5)), Image.BICUBIC))).permute(2, 0, 1)
+            assert torch.equal(got[n], want), (H, W, n, (got[n].int() - want.int()).abs().max())

@@ -1,0 +1,193 @@
+"""CPU: host-side logic of the product (no kernels launched) + the C-ABI surface."""
+import ctypes
+import hashlib
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+ROOT = util.ROOT
+
+
+def _digest(sd):
+    h = hashlib.sha256()
+    for k in sd:
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize('cfg,key', [('cr', 'l3c'), ('cr_rgb_shared', 'rgbs')])
+def test_state_dict_matches_reference(cfg, key):
+    """same keys, shapes, order and seed-0 default-init VALUES as the reference's module tree."""
+    bp = util.blueprint(cfg, device='cpu')
+    sd = bp.net.state_dict()
+    g = util.golden_summary()
+    assert sum(v.numel() for v in sd.values()) == g[key + '_sd_numel']
+    assert _digest(sd) == g[key + '_sd_sha256']
+    if key == 'l3c':
+        assert len(sd) == 268
+        for k, probe in g['l3c_sd_probe'].items():
+            np.testing.assert_allclose(sd[k].flatten()[:3].numpy(), probe, rtol=0, atol=0)
+
+
+def test_library_exports_every_declared_symbol():
+    from l3c_pytorch_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'l3c_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(l3c_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(_lib.SO_PATH)
+    for name in declared:
+        assert hasattr(lib, name), 'header declares %s but the library does not export it' % name
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    # the library is sm_100a code
+    out = subprocess.run(['cuobjdump', '-lelf', _lib.SO_PATH], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out
+
+
+def test_uniform_row_host_function_matches_oracle():
+    from l3c_pytorch_b200 import engine
+    from oracle import ac
+    for L in (25, 256, 5):
+        assert (engine.uniform_cdf_row(L) == ac.uniform_cdf_row(L)).all()
+
+
+def test_config_parser():
+    from l3c_pytorch_b200 import config
+    c = config.ms_config('cr')
+    assert (c.num_scales, c.Cf, c.q.C, c.q.L, c.prob.K, c.enc.num_blocks) == (3, 64, 5, 25, 10, 8)
+    assert c.q.levels_range == (-1, 1) and c.dec.skip is True and c.rgb_bicubic_baseline is False
+    s = config.ms_config('cr_rgb_shared')
+    assert (s.num_scales, s.q.C, s.enc.cls, s.dec.skip, s.enc.feed_F) == (1, 3, 'BicubicSubsampling', False, False)
+    assert s.Cf == 64 and s.rgb_bicubic_baseline is True            # inherited through `use cr.cf`
+    assert config.ms_config('cr_rgb').num_scales == 3
+
+
+def test_pad_matches_reference_rule():
+    from l3c_pytorch_b200 import pad
+    from oracle import model as om
+    for h, w in [(32, 32), (40, 28), (50, 30), (1500, 1000), (7, 9), (8, 15)]:
+        assert pad.padding_tuple(h, w, 8) == om.pad_tuple(h, w, 8)
+    x = torch.arange(3 * 50 * 30).reshape(1, 3, 50, 30)
+    y, t = pad.pad(x, 8, 'constant')
+    assert y.shape == (1, 3, 56, 32) and t == (1, 1, 3, 3)
+    assert (pad.undo_pad(y, *t) == x).all()
+    assert pad.padding_tuple(1500, 1000, 8) == (0, 0, 2, 2)          # 1504x1000
+
+
+def test_auto_crop_counts_and_stitch(monkeypatch):
+    from l3c_pytorch_b200 import auto_crop
+    for H, W, n in [(1000, 600, 64), (492, 326, 16), (204, 204, 4), (102, 102, 1)]:
+        img = (torch.rand(1, 3, H, W) * 255).round().long()
+        crops = list(auto_crop.iter_crops(img, 204 * 102))
+        assert len(crops) == n
+        if n > 1:
+            assert (auto_crop.stitch(crops) == img).all()
+    monkeypatch.setenv('AC_NEEDS_CROP_DIM', '40,40')
+    img = torch.zeros(1, 3, 100, 60)
+    assert auto_crop.needs_crop(img) and len(list(auto_crop.iter_crops(img))) == 4
+    monkeypatch.delenv('AC_NEEDS_CROP_DIM')
+    assert not auto_crop.needs_crop(torch.zeros(1, 3, 1500, 2000))
+    assert auto_crop.needs_crop(torch.zeros(1, 3, 3000, 2000))
+    c = auto_crop.CropLossCombinator()
+    c.add(2.0, 100)
+    c.add(4.0, 300)
+    assert abs(c.get_bpsp() - 3.5) < 1e-12
+
+
+def test_part_suffix(tmp_path):
+    from l3c_pytorch_b200 import part_suffix_helper as ps
+    assert ps.make_part_suffix(10) == '.part10'
+    assert ps.contains_part_suffix('a/b.part3') and not ps.contains_part_suffix('a/b.part3/more')
+    assert ps.index_of_part_suffix('a/b.part13') == 13
+    for i in range(16):
+        (tmp_path / ('some.file.part%d' % i)).write_text('x')
+    (tmp_path / 'some.file.partX').write_text('x')
+    got = ps.iter_part_suffixes(str(tmp_path / 'some.file.part3'))
+    assert [os.path.basename(p) for p in got] == ['some.file.part%d' % i for i in range(16)]
+
+
+def test_container_layout_roundtrip_and_reference_header():
+    from l3c_pytorch_b200.codec import ContainerLayout, parse_container, MAGIC
+    shapes = [(3, 5, 4, 4), (2, 5, 8, 8), (1, 5, 16, 16), (0, 3, 32, 32)]
+    lens = list(range(3, 21))
+    lay = ContainerLayout(shapes)
+    total, pieces, offs = lay.header_and_offsets(lens, (1, 2, 3, 4))
+    buf = bytearray(total)
+    for o, b in pieces:
+        buf[o:o + len(b)] = b
+    for o, n in zip(offs, lens):
+        buf[o:o + n] = bytes([n]) * n
+    pt, scales = parse_container(bytes(buf))
+    assert pt == (1, 2, 3, 4)
+    assert [(C, H, W) for (C, H, W, _) in scales] == [(5, 4, 4), (5, 8, 8), (5, 16, 16), (3, 32, 32)]
+    assert [n for s in scales for (_, n) in s[3]] == lens
+    assert total == 8 + 4 * (5 + 4) + 4 * 18 + sum(lens)
+    # a real file written by the reference parses, and its header equals what we would write
+    g = util.golden_npz('l3c_40x28_i1')
+    data = g['container'].tobytes()
+    pt, scales = parse_container(data)
+    assert pt == tuple(util.golden_summary()['l3c_40x28_i1']['pad'])
+    lens = [n for s in scales for (_, n) in s[3]]
+    shapes = [(3 - i, C, H, W) for i, (C, H, W, _) in enumerate(scales)]
+    total, pieces, offs = ContainerLayout(shapes).header_and_offsets(lens, pt)
+    assert total == len(data)
+    for o, b in pieces:
+        assert data[o:o + len(b)] == b
+    with pytest.raises(ValueError):
+        parse_container(data[:-1])
+    with pytest.raises(ValueError):
+        parse_container(data[:100])
+    assert MAGIC == bytes([0x46, 0xE2, 0x84, 0x92])
+
+
+def test_header_field_helpers(tmp_path):
+    from l3c_pytorch_b200 import bitcoding as bc
+    p = tmp_path / 'x.l3c'
+    with open(p, 'wb') as f:
+        bc.write_padding_tuple((1, 2, 3, 4), f)
+        bc.write_shape((1, 3, 512, 768), f)
+        bc.write_num_bytes_encoded(1234567, f)
+    with open(p, 'rb') as f:
+        assert bc.read_padding_tuple(f) == (1, 2, 3, 4)
+        assert bc.read_shapes(f) == (3, 512, 768)
+        assert bc.read_num_bytes_encoded(f) == 1234567
+    assert open(p, 'rb').read().hex() == '0100020003000400' + '03' + '0002' + '0003' + '87d61200'
+
+
+def test_torchac_shim_argument_errors():
+    """same exception types as the reference shim (torchac.py:93-94,127-131)."""
+    from l3c_pytorch_b200 import torchac
+    cdf = torch.zeros(1, 1, 2, 26, dtype=torch.int16)
+    if not torch.cuda.is_available():
+        with pytest.raises(ValueError):
+            torchac.encode_cdf(cdf, torch.zeros(2, dtype=torch.int16))      # no CPU backend: loud
+    t = torch.zeros(26)
+    with pytest.raises(ValueError):
+        torchac.encode_logistic_mixture(t, torch.zeros(1, 2, 1, 2), torch.zeros(1, 2, 1, 2),
+                                        torch.zeros(1, 2, 1, 2), torch.zeros(2, dtype=torch.int16))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'l3c_pytorch_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), fn
+                assert 'liboracle' not in src and 'oracle/' not in src.replace('oracle/ is', ''), fn
+
+
+def test_no_cpu_fallback_on_cpu_tensors():
+    from l3c_pytorch_b200 import engine
+    bp = util.blueprint('cr', device='cpu')
+    with pytest.raises(ValueError):
+        bp.net(torch.zeros(1, 3, 32, 32))
+    with pytest.raises(ValueError):
+        engine.conv2d(bp.net.heads[1].head, torch.zeros(1, 8, 8, 64))
