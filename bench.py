@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the L3C encode/decode hot path (see BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W                 (our sm_100a path, one process per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W (reference CPU path, host cores)
+
+One "step" = one lossless round trip (encode -> decode) of one batch of synthetic 3x512x512 images
+per GPU (BASELINE.json configs[1]: 16 images per GPU, L3C cr.cf, seed-0 default-init weights).
+Prints ONE JSON line (rank 0).  `value` = Mpixels/s with inputs resident in HBM; `e2e` = the same
+round trip through the public `Bitcoding.encode_batch/decode_batch` API from pinned host buffers
+(H2D of the images and the containers, D2H of the containers and the decoded images inside the
+timed region).  Timing: CUDA events on the launching stream, barrier + synchronize on both sides,
+max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'Mpixels/s encode+decode (lossless round-trip)'
+IMAGES_PER_GPU = 16
+HW = 512
+CONV_FLOP_PER_PX_ROUNDTRIP = 2.230e6      # 1.368 (encode forward) + 0.863 (decode)
+
+
+def make_images(first, n, hw=HW):
+    import torch
+    out = []
+    for i in range(first, first + n):
+        g = torch.Generator().manual_seed(1000 + i)
+        out.append((torch.rand(3, hw, hw, generator=g) * 255).round().to(torch.uint8))
+    return torch.stack(out)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for (t, line) in self.lines:
+            if t < t0 or t > t1 + 0.3:
+                continue
+            f = [x.strip() for x in line.split(',')]
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'],
+                                 f[4:8]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_roundtrip_mpx_s(n_images, hw, first_image=0):
+    """Round trip of `n_images` hw x hw images with the reference's CPU algorithm as restated in
+    oracle/model.py (byte-identical to the unmodified reference on the golden fixtures): PyTorch
+    fp32 CPU convs (all host threads), PyTorch CPU CDF tables (torchac.py:174-213), the reference's
+    own coder loop.  Returns (Mpx/s, seconds, bpsp, threads)."""
+    import torch
+    from l3c_pytorch_b200 import config
+    from l3c_pytorch_b200.blueprint import MultiscaleBlueprint
+    from oracle import model as om
+    torch.manual_seed(0)
+    bp = MultiscaleBlueprint(config.ms_config('cr'), device='cpu')
+    sd = {k: v.detach().cpu() for k, v in bp.net.state_dict().items()}
+    imgs = make_images(first_image, n_images, hw)
+    t0 = time.perf_counter()
+    total_bytes = 0
+    with torch.no_grad():
+        for i in range(n_images):
+            data = om.encode_image(sd, om.CFG_L3C, imgs[i], 'torch')
+            dec = om.decode_image(sd, om.CFG_L3C, data, 'torch')
+            assert bool((dec[0] == imgs[i].long()).all()), 'CPU reference round trip not lossless'
+            total_bytes += len(data)
+    dt = time.perf_counter() - t0
+    px = n_images * hw * hw
+    return px / 1e6 / dt, dt, total_bytes * 8 / (3 * px), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    import torch
+    steps, warm = args.steps, args.warmup
+    hw = HW if (steps + warm) <= 6 else 256          # keep the whole run within a few minutes
+    for _ in range(warm):
+        cpu_roundtrip_mpx_s(1, 128)
+    vals = []
+    t_all = 0.0
+    for s in range(steps):
+        v, dt, bpsp, thr = cpu_roundtrip_mpx_s(1, hw, first_image=s)
+        vals.append(v)
+        t_all += dt
+    px = steps * hw * hw
+    value = px / 1e6 / t_all
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'Mpixels/s', 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * t_all / steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'L3C cr.cf, %d x 3x512x512 per GPU, encode+decode round trip' % IMAGES_PER_GPU,
+                   'sample': '1 image of 3x%dx%d per step on the host CPU' % (hw, hw)},
+        'cpu_baseline': {'value': value, 'unit': 'Mpixels/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': '%d round trip(s) of one 3x%dx%d image (oracle/model.py, PyTorch-CPU CDF path, '
+                                   'byte-identical to the unmodified reference on tests/golden)' % (steps, hw, hw)},
+        'e2e': {'value': value, 'unit': 'Mpixels/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'bpsp': bpsp,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import l3c_pytorch_b200 as l3c
+    from l3c_pytorch_b200 import config, dist as l3c_dist, engine as E, _lib
+
+    rank, world, local_rank = l3c_dist.init_from_env()
+    assert torch.cuda.is_available(), 'bench.py (our arm) needs a GPU; there is no CPU fallback'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    E.set_conv_precision(args.precision)
+    torch.manual_seed(0)
+    bp = l3c.MultiscaleBlueprint(config.ms_config('cr'), device=dev).set_eval()
+    bc = l3c.Bitcoding(bp)
+    codec = bc.codec
+    n_img = args.images_per_gpu
+    n_global = n_img * world
+    lo, hi = l3c_dist.shard_bounds(n_global, rank, world)
+    # a few distinct batches so consecutive steps do not see identical inputs; activations are
+    # ~1 GB per layer at this batch size, far beyond the 126 MB L2
+    n_sets = 2
+    host_sets = [make_images(lo + s * n_global, n_img).pin_memory() for s in range(n_sets)]
+    dev_sets = [h.to(dev) for h in host_sets]
+    launches = {'n': 0}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(imgs):
+        blob, info = codec.encode_batch(imgs, to_host=False)
+        shapes = [(C, H, W) for (_, C, H, W) in info['shapes']]
+        S = codec.decode_device(blob, info['stream_offsets'], info['lens'], shapes)
+        return S, info
+
+    def step_e2e(host_imgs):
+        datas, bpsps = bc.encode_batch(host_imgs)
+        dec = bc.decode_batch(datas)
+        back = torch.cat(dec, 0).to(torch.uint8).cpu()        # D2H of the result
+        return back, datas
+
+    # ---- warm-up + correctness (outside the timed region)
+    for w in range(max(args.warmup, 1)):
+        S, info = step_resident(dev_sets[w % n_sets])
+    assert torch.equal(S, dev_sets[(max(args.warmup, 1) - 1) % n_sets]), 'round trip is not lossless'
+    sizes = info['sizes']
+    counts = l3c_dist.gather_byte_counts(sizes, n_global, rank, world)       # the one collective (NCCL)
+    bpsp = l3c_dist.global_bpsp(counts, 3 * HW * HW)
+
+    # ---- timed: device-resident
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        S, info = step_resident(dev_sets[s % n_sets])
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop(t_wall0, t_wall1)
+    ms_total = float(ms)
+    px_step_global = n_global * HW * HW
+    value = px_step_global * args.steps / 1e6 / (ms_total / 1e3)
+
+    # ---- timed: end to end through the public API (host buffers, copies inside)
+    back, datas = step_e2e(host_sets[0])
+    assert torch.equal(back, host_sets[0]), 'e2e round trip is not lossless'
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        back, datas = step_e2e(host_sets[s % n_sets])
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms2 = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = px_step_global * args.steps / 1e6 / (float(ms2) / 1e3)
+    cont_bytes = sum(len(d) for d in datas)
+    img_bytes = n_img * 3 * HW * HW
+
+    # ---- roofline of the dominant kernel: the 3x3 64->64 convolution at 256x256 (34 of the ~120
+    #      conv launches of a round trip and ~60 % of its FLOPs run on exactly this shape)
+    conv = bp.net.nets[0].enc.body[0].body[0]
+    x = torch.randn(n_img, HW // 2, HW // 2, 64, device=dev)
+    y = torch.empty_like(x)
+    for _ in range(3):
+        E.conv2d(conv, x, out=y)
+    torch.cuda.synchronize()
+    reps = 10
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(reps):
+        E.conv2d(conv, x, out=y)
+    c1.record()
+    torch.cuda.synchronize()
+    conv_ms = c0.elapsed_time(c1) / reps
+    conv_flops = 2.0 * 9 * 64 * 64 * n_img * (HW // 2) ** 2
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak_tf = peaks.get('bf16_tflops', 1590.0)
+    achieved_tf = conv_flops / (conv_ms / 1e3) / 1e12
+    roofline = {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                'frac': achieved_tf / peak_tf, 'traffic': None,
+                'kernel': 'conv3x3 64->64, %dx256x256 NHWC fp32 (%s path)' % (n_img, args.precision),
+                'peak_source': 'MEASURED_PEAKS.json bf16 burst' if peaks else 'fallback 1.59 PFLOP/s',
+                'whole_step_conv_tflops': CONV_FLOP_PER_PX_ROUNDTRIP * n_img * HW * HW * args.steps /
+                (ms_total / 1e3) / 1e12}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only, bounded sample)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt, cb, thr = cpu_roundtrip_mpx_s(1, HW)
+        cpu = {'value': v, 'unit': 'Mpixels/s', 'cores': thr, 'kind': 'port',
+               'sample': '1 round trip of one 3x512x512 image (%.1f s): oracle/model.py with the reference\'s '
+                         'PyTorch-CPU CDF path (byte-identical to the unmodified reference on tests/golden)' % dt,
+               'bpsp': cb}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'Mpixels/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'L3C cr.cf (3 scales, seed-0 default init), %d x 3x512x512 uint8 noise images '
+                                   'per GPU, encode+decode round trip, byte-compatible .l3c containers' % n_img,
+                       'global_batch': n_global, 'parallelism': 'images sharded over %d GPU(s), no data-path '
+                                                                'collective' % world,
+                       'conv_precision': args.precision,
+                       'l2': 'working set >> L2 (1 GB of activations per layer), inputs alternate between batches'},
+            'bpsp': bpsp,
+            'e2e': {'value': e2e_value, 'unit': 'Mpixels/s', 'h2d_bytes_per_step': img_bytes + cont_bytes,
+                    'd2h_bytes_per_step': cont_bytes + img_bytes},
+            'gpu_launches': None,
+            'clocks': clocks,
+            'roofline': roofline,
+            'cpu_baseline': cpu,
+        }
+        # launches: count them from the structure of one step (all are kernels of libl3c_b200.so)
+        line['gpu_launches'] = count_launches(bp) * args.steps
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def count_launches(bp):
+    """Kernels of libl3c_b200.so launched by one encode+decode round trip of one batch."""
+    net = bp.net
+    S = net.scales
+    convs_enc = 0 if net._rgb else S * (1 + 1 + 17)               # head, down, 8 ResBlocks*2 + 1
+    convs_dec = S * (1 + 17 + 1)                                    # head, body, tail
+    convs_prob = S * 4
+    fwd = (0 if net._rgb else 1) + convs_enc + S + convs_dec + convs_prob   # rgb_prep, quantize heads
+    enc_entropy = (S + 1) + 1 + 1                                   # intervals per scale, coder, gather
+    dec_net = convs_dec + convs_prob + S                            # + symbols_to_values
+    dec_entropy = 1 + (S - 1) * 2 + 3 * 2                           # uniform; z scales; RGB per channel
+    return fwd + enc_entropy + dec_net + dec_entropy
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', default=os.environ.get('L3C_CONV_PRECISION', 'fp32'),
+                    choices=['fp32', 'tf32', 'tf32x3', 'bf16'])
+    ap.add_argument('--images-per-gpu', type=int, default=IMAGES_PER_GPU)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -183,7 +183,7 @@ class BatchCodec(object):
             pos += (total + 15) & ~15
         blob = torch.empty(pos + 16, dtype=torch.uint8, device=dev)
         E.pack_streams(desc_dev, lens_dev, dst.reshape(-1), N * per_img, blob)
-        info = dict(sizes=sizes, starts=starts, lens=lens, shapes=shapes, out=out)
+        info = dict(sizes=sizes, starts=starts, lens=lens, shapes=shapes, out=out, stream_offsets=dst)
         if not to_host:
             return blob, info
         host = torch.empty(blob.shape, dtype=torch.uint8, pin_memory=True)
@@ -209,8 +209,6 @@ class BatchCodec(object):
         for p in parsed:
             if [(C, H, W) for (C, H, W, _) in p[1]] != ref_shapes:
                 raise ValueError('decode_batch needs containers of identical shape')
-        if len(ref_shapes) != self.net.scales + 1:
-            raise ValueError('container has %d scales, model expects %d' % (len(ref_shapes), self.net.scales + 1))
         # one upload of everything
         starts = np.zeros(N, np.int64)
         pos = 0
@@ -222,20 +220,35 @@ class BatchCodec(object):
         for n, dta in enumerate(datas):
             hb[starts[n]:starts[n] + len(dta)] = np.frombuffer(dta, np.uint8)
         blob = host.to(dev, non_blocking=True)
-        K = self.net.config_ms.prob.K
+        offs = np.array([[starts[n] + o for (_, _, _, st) in parsed[n][1] for (o, _) in st] for n in range(N)],
+                        np.int64)
+        lens = np.array([[ln for (_, _, _, st) in parsed[n][1] for (_, ln) in st] for n in range(N)], np.int64)
+        S = self.decode_device(blob, offs, lens, ref_shapes)
+        pads = [p[0] for p in parsed]
+        if to_host:
+            return S.cpu(), pads
+        return S, pads
 
+    def decode_device(self, blob, offs, lens, shapes):
+        """Decode streams that already sit in HBM: `blob` uint8 device buffer (readable 4 bytes past
+        every stream), offs/lens int64 [N][streams per image] in container order (coarse -> fine,
+        channel-major), shapes [(C,H,W)] coarse -> fine.  Returns uint8 [N,3,H,W] on the device."""
+        dev = blob.device
+        N = offs.shape[0]
+        if len(shapes) != self.net.scales + 1:
+            raise ValueError('container has %d scales, model expects %d' % (len(shapes), self.net.scales + 1))
+        K = self.net.config_ms.prob.K
         bn8, F_prev, S = None, None, None
+        j0 = 0
         for idx, (scale, dmll, uniform) in enumerate(self.iter_scale_dmll()):
-            C, H, W = ref_shapes[idx]
+            C, H, W = shapes[idx]
             HW = H * W
             S = torch.empty(N, C, H, W, dtype=torch.uint8, device=dev)
             desc = np.zeros(N * C, dtype=_lib.DEC_STREAM_DTYPE)
             d = desc.reshape(N, C)
-            for n in range(N):
-                for c in range(C):
-                    off, ln = parsed[n][1][idx][3][c]
-                    d['in'][n, c] = blob.data_ptr() + starts[n] + off
-                    d['in_len'][n, c] = ln
+            d['in'][:] = blob.data_ptr() + offs[:, j0:j0 + C]
+            d['in_len'][:] = lens[:, j0:j0 + C]
+            j0 += C
             d['n_sym'][:] = HW
             d['sym_out'][:] = S.data_ptr() + (np.arange(N)[:, None] * C + np.arange(C)[None, :]) * HW
             pitch = E.table_pitch(dmll.L)
@@ -262,7 +275,4 @@ class BatchCodec(object):
                     E.ac_decode_streams(desc, dev, dmll.L)
             if scale > 0:
                 bn8 = E.symbols_to_values(S, dmll.values(dev), self._rgb_shift(dev))
-        pads = [p[0] for p in parsed]
-        if to_host:
-            return S.cpu(), pads
-        return S, pads
+        return S

@@ -190,10 +190,10 @@ struct BitSource {
     }
 };
 
-template <int EPL>
+template <int EPL, bool FULLROW>
 struct RowRegs;
-template <>
-struct RowRegs<8> {
+template <bool FULLROW>
+struct RowRegs<8, FULLROW> {
     uint4 v;
     __device__ __forceinline__ void load(const uint16_t *row, int lane, int /*L*/) {
         v = __ldg(reinterpret_cast<const uint4 *>(row) + lane);
@@ -201,19 +201,91 @@ struct RowRegs<8> {
     __device__ __forceinline__ uint32_t get(int j, int lane, int L) const {
         const uint32_t w = (j < 2) ? v.x : (j < 4) ? v.y : (j < 6) ? v.z : v.w;
         const uint32_t e = (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+        if (FULLROW) return e;
         return (lane * 8 + j < L) ? e : 0x10000u;       // padding entries never compare true
     }
 };
-template <>
-struct RowRegs<1> {
+template <bool FULLROW>
+struct RowRegs<1, FULLROW> {
     uint32_t v;
     __device__ __forceinline__ void load(const uint16_t *row, int lane, int L) {
-        v = (lane < L) ? (uint32_t)__ldg(row + lane) : 0x10000u;
+        v = (FULLROW || lane < L) ? (uint32_t)__ldg(row + lane) : 0x10000u;
     }
     __device__ __forceinline__ uint32_t get(int, int, int) const { return v; }
 };
 
-template <int EPL>
+// count of torchac.cpp:327 in the reference's modular 64-bit arithmetic (only needed when the code
+// value has left [low, high], i.e. on corrupt or foreign input) -- kept out of line on purpose
+__device__ __noinline__ uint32_t foreign_count16(uint32_t value, uint32_t low, uint32_t r) {
+    const uint64_t off = (uint64_t)value - (uint64_t)low + 1ull;
+    return (uint32_t)(((off * 65536ull - 1ull) / ((uint64_t)r + 1ull)) & 0xFFFFull);
+}
+
+struct CoderState {
+    uint32_t low, high, value;
+};
+
+// one symbol: search the row, update [low, high], renormalise, shift code bits into `value`
+template <int EPL, bool FULLROW>
+__device__ __forceinline__ int decode_step(const RowRegs<EPL, FULLROW> &cur, CoderState &cs, BitSource &src,
+                                           int lane, int L, bool update) {
+    const uint32_t r = cs.high - cs.low;                        // span - 1
+    const uint32_t dv = cs.value - cs.low;
+    const uint64_t target = ((uint64_t)dv + 1ull) << 16;
+    uint32_t lane_lo = 0u, lane_hi = 0x10000u;
+    int n_true = 0;
+    if (__builtin_expect(dv > r, 0)) {
+        // value outside [low, high]: reproduce the reference's arithmetic exactly
+        const uint32_t count16 = foreign_count16(cs.value, cs.low, r);
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            const uint32_t e = cur.get(j, lane, L);
+            const bool f = (e <= count16) || (j == 0 && lane == 0);
+            lane_lo = f ? max(lane_lo, e) : lane_lo;
+            lane_hi = f ? lane_hi : min(lane_hi, e);
+            n_true += f ? 1 : 0;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            const uint32_t e = cur.get(j, lane, L);
+            const uint64_t prod = (uint64_t)r * e + e;          // e * span
+            const bool f = (prod < target) || (j == 0 && lane == 0);   // cdf[m] <= count; symbol 0 = floor
+            lane_lo = f ? max(lane_lo, e) : lane_lo;
+            lane_hi = f ? lane_hi : min(lane_hi, e);
+            n_true += f ? 1 : 0;
+        }
+    }
+    const uint32_t c_lo = __reduce_max_sync(FULL, lane_lo);
+    const uint32_t c_hi = __reduce_min_sync(FULL, lane_hi);
+    const int sym = __reduce_add_sync(FULL, n_true) - 1;
+    if (update) {
+        const uint64_t p_hi = (uint64_t)r * c_hi + c_hi;
+        const uint64_t p_lo = (uint64_t)r * c_lo + c_lo;
+        uint32_t high = cs.low - 1u + (uint32_t)(p_hi >> 16);
+        uint32_t low = cs.low + (uint32_t)(p_lo >> 16);
+        uint32_t value = cs.value;
+        const int k = __clz((int)(low ^ high));
+        if (k > 0) {
+            low <<= k;
+            high = (high << k) | ((1u << k) - 1u);
+            value = (value << k) | src.take(k);
+        }
+        const uint32_t m = (low & ~high) << 1;
+        const int u = __clz((int)~m);
+        if (u > 0) {
+            low = (low << u) & 0x7FFFFFFFu;
+            high = (high << u) | 0x80000000u | ((1u << u) - 1u);
+            value = ((value << u) | src.take(u)) ^ 0x80000000u;
+        }
+        cs.low = low;
+        cs.high = high;
+        cs.value = value;
+    }
+    return sym;
+}
+
+template <int EPL, bool FULLROW>
 __global__ void __launch_bounds__(32 * DEC_WARPS_PER_CTA)
 ac_decode_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, int L,
                  uint32_t first, uint32_t count) {
@@ -229,82 +301,59 @@ ac_decode_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, in
     BitSource src;
     src.open(st.in, st.in_len);
 
-    uint32_t low, high, value;
+    CoderState cs;
     if (first == 0) {
-        low = 0u;
-        high = 0xFFFFFFFFu;
+        cs.low = 0u;
+        cs.high = 0xFFFFFFFFu;
         src.seek(0);
-        value = src.take(32);
+        cs.value = src.take(32);
     } else {
-        low = st.state[0];
-        high = st.state[1];
-        value = st.state[2];
+        cs.low = st.state[0];
+        cs.high = st.state[1];
+        cs.value = st.state[2];
         src.seek(st.state[3]);
     }
 
     const uint16_t *__restrict__ table = st.table;
     const int64_t pitch = st.row_pitch;
+    uint8_t *__restrict__ sym_out = st.sym_out;
 
-    RowRegs<EPL> ring[D];
+    // symbols handled by the unrolled main loop: whole groups of D, never the stream's final symbol
+    const uint32_t upd_end = (last == n) ? n - 1 : last;          // symbols < upd_end update the state
+    const uint32_t main_end = first + ((upd_end - first) / D) * D;
+
+    RowRegs<EPL, FULLROW> ring[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const uint32_t i = first + d;
         if (i < last) ring[d].load(table + (int64_t)i * pitch, lane, L);
     }
-
-    for (uint32_t base = first; base < last; base += D) {
+    uint32_t base = first;
+    for (; base < main_end; base += D) {
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             const uint32_t i = base + d;
-            if (i >= last) break;
-            const RowRegs<EPL> cur = ring[d];
+            const RowRegs<EPL, FULLROW> cur = ring[d];
             if (i + D < last) ring[d].load(table + (int64_t)(i + D) * pitch, lane, L);
-
-            const uint32_t r = high - low;                              // span - 1
-            const uint64_t target = ((uint64_t)(value - low) + 1ull) << 16;
-            uint32_t lane_lo = 0u, lane_hi = 0x10000u;
-            int n_true = 0;
+            const int sym = decode_step<EPL, FULLROW>(cur, cs, src, lane, L, true);
+            if (lane == 0) sym_out[i] = (uint8_t)sym;
+        }
+    }
+    // tail (< D symbols, may contain the final symbol, which leaves the state untouched:
+    // torchac.cpp:335-337)
 #pragma unroll
-            for (int j = 0; j < EPL; ++j) {
-                const uint32_t e = cur.get(j, lane, L);
-                const uint64_t prod = (uint64_t)r * e + e;              // e * span
-                bool f = prod < target;                                 // cdf[m] <= count
-                if (j == 0 && lane == 0) f = true;                      // symbol 0 is the floor
-                lane_lo = f ? max(lane_lo, e) : lane_lo;
-                lane_hi = f ? lane_hi : min(lane_hi, e);
-                n_true += f ? 1 : 0;
-            }
-            const uint32_t c_lo = __reduce_max_sync(FULL, lane_lo);
-            const uint32_t c_hi = __reduce_min_sync(FULL, lane_hi);
-            const int sym = __reduce_add_sync(FULL, n_true) - 1;
-            if (lane == 0) st.sym_out[i] = (uint8_t)sym;
-            if (i == n - 1) break;                                      // torchac.cpp:335-337
-
-            const uint64_t p_hi = (uint64_t)r * c_hi + c_hi;
-            const uint64_t p_lo = (uint64_t)r * c_lo + c_lo;
-            high = low - 1u + (uint32_t)(p_hi >> 16);
-            low = low + (uint32_t)(p_lo >> 16);
-
-            const int k = __clz((int)(low ^ high));
-            if (k > 0) {
-                low <<= k;
-                high = (high << k) | ((1u << k) - 1u);
-                value = (value << k) | src.take(k);
-            }
-            const uint32_t m = (low & ~high) << 1;
-            const int u = __clz((int)~m);
-            if (u > 0) {
-                low = (low << u) & 0x7FFFFFFFu;
-                high = (high << u) | 0x80000000u | ((1u << u) - 1u);
-                value = ((value << u) | src.take(u)) ^ 0x80000000u;
-            }
+    for (int d = 0; d < D; ++d) {
+        const uint32_t i = base + d;
+        if (i < last) {
+            const int sym = decode_step<EPL, FULLROW>(ring[d], cs, src, lane, L, i < upd_end);
+            if (lane == 0) sym_out[i] = (uint8_t)sym;
         }
     }
 
     if (lane == 0 && st.state != nullptr) {
-        st.state[0] = low;
-        st.state[1] = high;
-        st.state[2] = value;
+        st.state[0] = cs.low;
+        st.state[1] = cs.high;
+        st.state[2] = cs.value;
         st.state[3] = src.consumed;
     }
 }
@@ -358,12 +407,16 @@ extern "C" int l3c_ac_decode_streams(const l3c_dec_stream_t *streams_dev, int n_
     if (n_streams == 0 || count == 0) return L3C_OK;
     L3C_REQUIRE(streams_dev, "l3c_ac_decode_streams: null pointer");
     const int grid = ceil_div(n_streams, DEC_WARPS_PER_CTA);
-    if (L <= 32) {
-        ac_decode_kernel<1><<<grid, 32 * DEC_WARPS_PER_CTA, 0, (cudaStream_t)stream>>>(
-            streams_dev, n_streams, L, first, count);
+    const dim3 blk(32 * DEC_WARPS_PER_CTA);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (L == 32) {
+        ac_decode_kernel<1, true><<<grid, blk, 0, st>>>(streams_dev, n_streams, L, first, count);
+    } else if (L < 32) {
+        ac_decode_kernel<1, false><<<grid, blk, 0, st>>>(streams_dev, n_streams, L, first, count);
+    } else if (L == 256) {
+        ac_decode_kernel<8, true><<<grid, blk, 0, st>>>(streams_dev, n_streams, L, first, count);
     } else {
-        ac_decode_kernel<8><<<grid, 32 * DEC_WARPS_PER_CTA, 0, (cudaStream_t)stream>>>(
-            streams_dev, n_streams, L, first, count);
+        ac_decode_kernel<8, false><<<grid, blk, 0, st>>>(streams_dev, n_streams, L, first, count);
     }
     L3C_LAUNCH_CHECK("ac_decode_kernel");
     return L3C_OK;

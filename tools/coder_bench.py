@@ -1,0 +1,55 @@
+"""Micro-benchmark of the range-coder kernels alone: ns per symbol per stream."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from l3c_pytorch_b200 import engine as E, _lib
+
+def run(L, n_streams, n_sym, peaked):
+    dev = torch.device('cuda')
+    rng = np.random.default_rng(0)
+    pitch = E.table_pitch(L)
+    # one random table shared by all streams (content is irrelevant for timing, sizes are not)
+    w = rng.integers(1, 40, size=(n_sym, L)).astype(np.float64)
+    if peaked:
+        w[np.arange(n_sym), rng.integers(0, L, n_sym)] *= 2000
+    w = w / w.sum(1, keepdims=True) * (65536 - L - 40)
+    c = np.floor(np.cumsum(w, 1)).astype(np.int64) + np.arange(1, L + 1)
+    cdf = np.concatenate([np.zeros((n_sym, 1), np.int64), c[:, :-1]], 1)          # [n_sym, L]
+    hi_all = np.concatenate([cdf[:, 1:], np.full((n_sym, 1), 65536)], 1)
+    sym = np.array([rng.choice(L, p=(wi / wi.sum())) for wi in w[:2000]])
+    sym = np.resize(sym, n_sym).astype(np.int64)
+    lo = cdf[np.arange(n_sym), sym]; hi = hi_all[np.arange(n_sym), sym]
+    iv = torch.from_numpy((lo | ((hi - 1) << 16)).astype(np.uint32).view(np.int32)).to(dev)
+    tab = np.zeros((n_sym, pitch), np.uint16); tab[:, :L] = cdf
+    tab_dev = torch.from_numpy(tab.view(np.int16)).to(dev)
+    cap = ((n_sym * 17 + 7) // 8 + 64 + 3) & ~3
+    slots = torch.zeros(n_streams * cap, dtype=torch.uint8, device=dev)
+    desc = np.zeros(n_streams, dtype=_lib.ENC_STREAM_DTYPE)
+    desc['intervals'] = iv.data_ptr(); desc['n_sym'] = n_sym; desc['out_cap'] = cap
+    desc['out'] = slots.data_ptr() + cap * np.arange(n_streams)
+    def timed(fn, reps=3):
+        best = 1e9
+        for _ in range(reps):
+            torch.cuda.synchronize(); a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize(); best = min(best, a.elapsed_time(b))
+        return best
+    ddev = E._desc_to_device(desc, dev)
+    lens = torch.empty(n_streams, dtype=torch.int32, device=dev)
+    t_enc = timed(lambda: E.check(E.lib.l3c_ac_encode_streams(E._ptr(ddev), n_streams, E._ptr(lens), E._stream_ptr())))
+    nbytes = int(lens[0])
+    out = torch.zeros(n_streams * n_sym, dtype=torch.uint8, device=dev)
+    dd = np.zeros(n_streams, dtype=_lib.DEC_STREAM_DTYPE)
+    dd['table'] = tab_dev.data_ptr(); dd['in'] = slots.data_ptr() + cap * np.arange(n_streams)
+    dd['sym_out'] = out.data_ptr() + n_sym * np.arange(n_streams); dd['row_pitch'] = pitch
+    dd['n_sym'] = n_sym; dd['in_len'] = nbytes
+    dddev = E._desc_to_device(dd, dev)
+    t_dec = timed(lambda: E.check(E.lib.l3c_ac_decode_streams(E._ptr(dddev), n_streams, L, 0, n_sym, E._stream_ptr())))
+    ok = bool((out.reshape(n_streams, n_sym).cpu().numpy() == sym[None, :]).all())
+    print(json.dumps(dict(L=L, streams=n_streams, n_sym=n_sym, peaked=peaked, bits_per_sym=nbytes * 8 / n_sym,
+                          enc_ns_per_sym=t_enc * 1e6 / n_sym, dec_ns_per_sym=t_dec * 1e6 / n_sym, ok=ok)))
+
+if __name__ == '__main__':
+    for (L, ns, n, pk) in [(256, 4, 65536, False), (256, 48, 65536, True), (256, 1024, 16384, True),
+                           (25, 80, 65536, True), (25, 2048, 8192, True)]:
+        run(L, ns, n, pk)
