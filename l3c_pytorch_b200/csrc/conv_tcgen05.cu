@@ -1,10 +1,403 @@
-// conv_tcgen05.cu -- tensor-core (tcgen05 + TMA + TMEM) implicit-GEMM convolution.  Placeholder
-// until the kernel lands: the dispatcher fails loudly instead of silently falling back.
+// conv_tcgen05.cu -- 3x3 (optionally dilated) 64-input-channel convolution as an implicit GEMM on the
+// Blackwell 5th-generation tensor cores: TMA (cp.async.bulk.tensor) stages shifted NHWC windows and
+// weight slabs into 128B-swizzled shared memory, ONE elected thread issues tcgen05.mma (kind::tf32,
+// M=128 pixels x N=64 output channels x K=8), accumulators live in TMEM (two 64-column buffers so
+// the epilogue of tile i overlaps the MMAs of tile i+1), a 4-warp epilogue drains TMEM with
+// tcgen05.ld and fuses bias / ReLU / residual / channel-slice / PixelShuffle(2).
+//
+// Reference layers this replaces: every `default_conv(64, Cout, 3, rate=r)` of the L3C stack
+// (/root/reference/src/pytorch_ext.py:57-61; ResBlock edsr.py:63-89, body-final conv net.py:110,170,
+// Head head.py:49-56, Upsampler edsr.py:92-101, atrous convs prob_clf.py:54-55) -- cuDNN fp32 in the
+// reference.
+//
+// Implicit GEMM mapping (per 8x16-pixel tile, per filter tap t=(ky,kx)):
+//   A[m][k] = x[n, ty0 + m/16 + (ky-1)*d, tx0 + m%16 + (kx-1)*d, k]   (zero outside the image: TMA
+//             out-of-bounds fill implements the conv padding), m = 0..127, k = 0..63
+//   B[n][k] = w[n, k, ky, kx]                                          n = 0..63 (one Cout tile)
+//   D[m][n] += sum_k A[m][k] * B[n][k]        -> 9 taps x 2 K-halves x 4 tcgen05.mma (K=8 tf32 each)
+// Accumulation order per output element is fixed (tap, K-half, k-step), independent of batch,
+// image size and tile position: encoder-side and decoder-side evaluations are bit-identical.
+//
+// Precision modes: L3C_PREC_TF32 feeds fp32 activations/weights straight to kind::tf32 (the tensor
+// core reads the upper 19 bits), fp32 accumulate.  (3xTF32 / bf16 are not built yet: the dispatcher
+// says so loudly.)
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace l3c {
-int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t) {
-    set_error("l3c_conv2d: precision mode %d (tcgen05) is not built yet", p.precision);
-    return L3C_EINVAL;
+
+int conv2d_ffma(const l3c_conv_t &p, cudaStream_t st);
+
+namespace tc {
+
+constexpr int TH = 8, TW = 16;                 // 128 output pixels = UMMA M
+constexpr int STAGES = 4;
+constexpr int A_HALF = 128 * 128;              // 128 pixel rows x 128 B (32 fp32 channels)
+constexpr int B_HALF = 64 * 128;               // 64 cout rows x 128 B
+constexpr int STAGE_BYTES = 2 * A_HALF + 2 * B_HALF;   // 48 KB per filter tap
+constexpr int THREADS = 192;                   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int ACC_COLS = 64;
+constexpr int TMEM_COLS = 128;                 // two accumulators
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 256 /*bias*/;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu)      // start address
+           | (1ull << 16)                              // leading byte offset (16 B, unused for SW128 K-major)
+           | (64ull << 32)                             // stride byte offset: 1024 B between 8-row groups
+           | (1ull << 46)                              // descriptor version (Blackwell)
+           | (2ull << 61);                             // SWIZZLE_128B
+}
+
+// instruction descriptor: D=f32, A=B=tf32, both K-major, N=64, M=128
+constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct Params {
+    const float *bias;      // padded to cout_pad
+    const float *residual;
+    float *y;
+    int N, H, W;
+    int Cout, y_pitch, y_coff;
+    int dilation;
+    unsigned flags;
+    int tiles_x, tiles_y, cout_tiles, total_tiles;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                       const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 128B swizzle atoms need 1024 B alignment
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    // bars[0..3] full, [4..7] empty, [8..9] tmem_full, [10..11] tmem_empty
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
+    float *s_bias = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (8 + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (10 + a); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);          // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int d = p.dilation;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        uint32_t stage = 0, phase = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            int q = t;
+            const int ct = q % p.cout_tiles; q /= p.cout_tiles;
+            const int tx = q % p.tiles_x; q /= p.tiles_x;
+            const int ty = q % p.tiles_y; q /= p.tiles_y;
+            const int n = q;
+            for (int tap = 0; tap < 9; ++tap) {
+                if (lane == 0) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    const uint32_t a0 = smem_base + stage * STAGE_BYTES;
+                    const int x0 = tx * TW + (tap % 3 - 1) * d;
+                    const int y0 = ty * TH + (tap / 3 - 1) * d;
+                    tma_load_4d(a0, &map_x, full_bar(stage), 0, x0, y0, n);
+                    tma_load_4d(a0 + A_HALF, &map_x, full_bar(stage), 32, x0, y0, n);
+                    const int wrow = (tap * 2) * p.cout_tiles * 64 + ct * 64;   // rows: [tap][khalf][cout]
+                    tma_load_2d(a0 + 2 * A_HALF, &map_w, full_bar(stage), 0, wrow);
+                    tma_load_2d(a0 + 2 * A_HALF + B_HALF, &map_w, full_bar(stage), 0, wrow + p.cout_tiles * 64);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        uint32_t stage = 0, phase = 0;
+        uint32_t acc = 0, acc_phase = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            if (lane == 0) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);       // epilogue has drained this accumulator
+                tc_fence_after();
+            }
+            __syncwarp();
+            const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+            for (int tap = 0; tap < 9; ++tap) {
+                if (lane == 0) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_base + stage * STAGE_BYTES;
+#pragma unroll
+                    for (int kh = 0; kh < 2; ++kh) {
+                        const uint64_t da = make_desc(a0 + kh * A_HALF);
+                        const uint64_t db = make_desc(a0 + 2 * A_HALF + kh * B_HALF);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            // +32 B (8 tf32) along K inside the 128 B swizzle row: +2 in 16-byte units
+                            mma_tf32(d_tmem, da + 2u * k, db + 2u * k, IDESC_TF32,
+                                     (tap | kh | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    mma_commit(empty_bar(stage));                 // frees the smem slot when the MMAs retire
+                    if (tap == 8) mma_commit(tfull_bar(acc));     // accumulator complete -> epilogue
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 are this warp's
+        const int m = quarter * 32 + lane;            // pixel row of the tile
+        uint32_t acc = 0, acc_phase = 0;
+        const bool relu = (p.flags & L3C_CONV_RELU) != 0;
+        const bool shuffle = (p.flags & L3C_CONV_PIXEL_SHUFFLE2) != 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            int q = t;
+            const int ct = q % p.cout_tiles; q /= p.cout_tiles;
+            const int tx = q % p.tiles_x; q /= p.tiles_x;
+            const int ty = q % p.tiles_y; q /= p.tiles_y;
+            const int n = q;
+            const int oy = ty * TH + (m >> 4);
+            const int ox = tx * TW + (m & 15);
+            const bool inside = (oy < p.H) && (ox < p.W);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                if (inside) {
+                    const int co0 = ct * 64 + c0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        v[i] += __ldg(p.bias + co0 + i);
+                        if (relu) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    if (!shuffle) {
+                        const size_t off = (((size_t)n * p.H + oy) * p.W + ox) * p.y_pitch + p.y_coff + co0;
+                        if (p.residual) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 r = __ldg(reinterpret_cast<const float4 *>(p.residual + off + i));
+                                v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4 *>(p.y + off + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+                        // out[n, 2*oy+i, 2*ox+j, cq] = conv[n, oy, ox, 4*cq + 2*i + j]
+                        const int H2 = p.H * 2, W2 = p.W * 2;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int co = co0 + i;
+                            const int cq = co >> 2, si = (co >> 1) & 1, sj = co & 1;
+                            p.y[(((size_t)n * H2 + 2 * oy + si) * W2 + 2 * ox + sj) * p.y_pitch + p.y_coff + cq] = v[i];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+    (void)s_bias;
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+}  // namespace tc
+
+int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st) {
+    using namespace tc;
+    if (p.precision != L3C_PREC_TF32) {
+        set_error("l3c_conv2d: precision mode %d is not built (available: fp32, tf32)", p.precision);
+        return L3C_EINVAL;
+    }
+    // The tensor-core kernel covers the 3x3 / 64-input-channel layers (> 92 % of the FLOPs of a round
+    // trip).  The host mirror routes the other layers (5x5/s2 down-sampling, 1x1 convs, Cin != 64) to
+    // L3C_PREC_FP32 explicitly (engine.conv2d); nothing falls back silently here.
+    const bool eligible = p.ksize == 3 && p.stride == 1 && p.Cin == 64 && p.x_pitch == 64 && p.Cout % 64 == 0 &&
+                          (p.y_pitch % 4 == 0) && (p.y_coff % 4 == 0);
+    L3C_REQUIRE(eligible, "l3c_conv2d: tcgen05 path needs ksize=3 stride=1 Cin=x_pitch=64 Cout%%64==0 "
+                          "(got k=%d s=%d Cin=%d pitch=%d Cout=%d)", p.ksize, p.stride, p.Cin, p.x_pitch, p.Cout);
+
+    EncodeTiledFn encode = get_encode_fn();
+    L3C_REQUIRE(encode != nullptr, "l3c_conv2d: cuTensorMapEncodeTiled is not available from the driver");
+
+    alignas(64) CUtensorMap map_x, map_w;
+    {
+        cuuint64_t dims[4] = {64, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+        cuuint64_t strides[3] = {(cuuint64_t)p.x_pitch * 4, (cuuint64_t)p.W * p.x_pitch * 4,
+                                 (cuuint64_t)p.H * p.W * p.x_pitch * 4};
+        cuuint32_t box[4] = {32, TW, TH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(p.x), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        L3C_REQUIRE(r == CUDA_SUCCESS, "l3c_conv2d: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+    }
+    const int cout_tiles = p.Cout / 64;
+    {
+        // tensor-core weight image: [tap 9][K-half 2][Cout][32] fp32 (see engine.PackedConv.get_tc)
+        cuuint64_t dims[2] = {32, (cuuint64_t)(9 * 2 * p.Cout)};
+        cuuint64_t strides[1] = {128};
+        cuuint32_t box[2] = {32, 64};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p.w), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        L3C_REQUIRE(r == CUDA_SUCCESS, "l3c_conv2d: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
+    }
+    Params q;
+    q.bias = p.bias;
+    q.residual = p.residual;
+    q.y = p.y;
+    q.N = p.N; q.H = p.H; q.W = p.W;
+    q.Cout = p.Cout; q.y_pitch = p.y_pitch; q.y_coff = p.y_coff;
+    q.dilation = p.dilation;
+    q.flags = p.flags;
+    q.tiles_x = ceil_div(p.W, TW);
+    q.tiles_y = ceil_div(p.H, TH);
+    q.cout_tiles = cout_tiles;
+    q.total_tiles = p.N * q.tiles_x * q.tiles_y * cout_tiles;
+
+    static int n_sm = 0;
+    static bool configured = false;
+    if (!configured) {
+        int dev = 0;
+        L3C_CUDA(cudaGetDevice(&dev));
+        L3C_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        L3C_CUDA(cudaFuncSetAttribute(conv3x3_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int grid = q.total_tiles < n_sm ? q.total_tiles : n_sm;      // persistent: one CTA per SM
+    conv3x3_tcgen05_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(map_x, map_w, q);
+    L3C_LAUNCH_CHECK("conv3x3_tcgen05_kernel");
+    return L3C_OK;
+}
+
 }  // namespace l3c

@@ -60,15 +60,38 @@ class PackedConv(object):
             bp = torch.zeros(cout_pad, dtype=torch.float32, device=w.device)
             bp[:cout] = b.detach().float()
             self.w, self.b, self._key = wp, bp, key
+            self.w_tc = None
         return self.w, self.b
 
+    def get_tc(self):
+        """Tensor-core operand image of a 3x3 / 64-input-channel conv: [tap 9][K-half 2][Cout][32]
+        fp32, K-major rows of 128 B that TMA drops into 128B-swizzled shared memory."""
+        _, b = self.get()
+        if self.w_tc is None:
+            w = self.conv.weight.detach().float()
+            cout, cin, kh, kw = w.shape
+            assert (cin, kh, kw) == (64, 3, 3)
+            self.w_tc = w.permute(2, 3, 0, 1).reshape(9, cout, 2, 32).permute(0, 2, 1, 3).contiguous()
+        return self.w_tc, b
 
-def packed(conv):
+
+def _packed_obj(conv):
     pc = conv.__dict__.get('_l3c_packed')
     if pc is None:
         pc = PackedConv(conv)
         conv.__dict__['_l3c_packed'] = pc
-    return pc.get()
+    return pc
+
+
+def packed(conv):
+    return _packed_obj(conv).get()
+
+
+def tc_eligible(conv, x_pitch, y_pitch, y_coff):
+    """Layers the tcgen05 kernel covers: 3x3 (any dilation), stride 1, 64 input channels in a
+    pitch-64 buffer, Cout a multiple of 64.  Everything else runs on the fp32 FFMA kernel."""
+    return (conv.kernel_size[0] == 3 and conv.stride[0] == 1 and conv.in_channels == 64 and x_pitch == 64 and
+            conv.out_channels % 64 == 0 and y_pitch % 4 == 0 and y_coff % 4 == 0)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -81,7 +104,6 @@ def conv2d(conv, x, cin=None, relu=False, residual=None, pixel_shuffle=False, ou
     (used for the atrous concat, prob_clf.py:71)."""
     require_cuda(x, 'x')
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
-    w, b = packed(conv)
     N, H, W, xp = x.shape
     kh = conv.kernel_size[0]
     stride, dil = conv.stride[0], conv.dilation[0]
@@ -96,11 +118,17 @@ def conv2d(conv, x, cin=None, relu=False, residual=None, pixel_shuffle=False, ou
             out = torch.empty(N, Ho * 2, Wo * 2, cout // 4, dtype=torch.float32, device=x.device)
         else:
             out = torch.empty(N, Ho, Wo, cout, dtype=torch.float32, device=x.device)
+    prec = _PRECISION['mode'] if precision is None else precision
+    if prec != _lib.PREC_FP32 and tc_eligible(conv, xp, out.shape[-1], out_coff) and cin == 64:
+        w, b = _packed_obj(conv).get_tc()
+    else:
+        prec = _lib.PREC_FP32
+        w, b = packed(conv)
     d = ConvDesc(x=x.data_ptr(), w=w.data_ptr(), bias=b.data_ptr(),
                  residual=residual.data_ptr() if residual is not None else None, y=out.data_ptr(),
-                 N=N, H=H, W=W, Cin=cin, x_pitch=xp, Cout=cout, cout_pad=w.shape[-1],
+                 N=N, H=H, W=W, Cin=cin, x_pitch=xp, Cout=cout, cout_pad=b.shape[0],
                  y_pitch=out.shape[-1], y_coff=out_coff, ksize=kh, stride=stride, dilation=dil,
-                 flags=flags, precision=_PRECISION['mode'] if precision is None else precision)
+                 flags=flags, precision=prec)
     if residual is not None:
         assert residual.shape == out.shape and residual.is_contiguous()
     check(lib.l3c_conv2d(ctypes.byref(d), _stream_ptr()))
