@@ -168,9 +168,10 @@ int l3c_dmll_channel_params(const float *l_dev, const float *x_dec_dev, int N, i
 
 #define L3C_CONV_RELU 1u            /* y = max(y, 0) after bias                                  */
 #define L3C_CONV_PIXEL_SHUFFLE2 2u  /* out[n,2h+i,2w+j,c] = y[n,h,w,4c+2i+j] (edsr.py:92-101)     */
+#define L3C_CONV_ROUND_TF32 4u      /* round y itself to TF32 (cvt.rna): y only feeds tensor-core convs */
 
 #define L3C_PREC_FP32 0             /* CUDA-core FFMA, fp32 throughout (bit-faithful ordering)    */
-#define L3C_PREC_TF32 1             /* tcgen05 kind::tf32, fp32 accumulate in TMEM                */
+#define L3C_PREC_TF32 1             /* tcgen05 kind::tf32 on operands pre-rounded to TF32 (RN), fp32 accumulate in TMEM */
 #define L3C_PREC_TF32X3 2           /* tcgen05, error-compensated 3xTF32 split (~fp32 accuracy)   */
 #define L3C_PREC_BF16 3             /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate         */
 
@@ -180,6 +181,8 @@ typedef struct {
     const float *bias;     /* dev [cout_pad]                                                       */
     const float *residual; /* dev NHWC like the output (same pitch/offset), or NULL: y += res      */
     float *y;              /* dev NHWC [N][Ho][Wo][y_pitch], channels [y_coff, y_coff+Cout) written */
+    float *y_tf32;         /* optional second output, same layout as y: the result rounded to TF32     */
+                           /* (round-to-nearest) = operand image for a following tensor-core conv; NULL ok */
     int N, H, W, Cin, x_pitch;
     int Cout, cout_pad, y_pitch, y_coff;
     int ksize, stride, dilation;   /* padding = ksize/2 if dilation==1 else dilation               */

@@ -33,6 +33,11 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
+__device__ __forceinline__ float round_tf32(float x) {      // round-to-nearest TF32 image of x
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
@@ -147,6 +152,7 @@ conv_ffma_kernel(l3c_conv_t p, int Ho, int Wo, int tiles_x, int pad) {
     if (oy >= Ho) return;
     const bool relu = (p.flags & L3C_CONV_RELU) != 0;
     const bool shuffle = (p.flags & L3C_CONV_PIXEL_SHUFFLE2) != 0;
+    const bool round_y = (p.flags & L3C_CONV_ROUND_TF32) != 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int ox = ox0 + 2 * j + phalf;
@@ -167,6 +173,16 @@ conv_ffma_kernel(l3c_conv_t p, int Ho, int Wo, int tiles_x, int pad) {
                     v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
                     v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
                 }
+                if (p.y_tf32) {
+                    *reinterpret_cast<float4 *>(p.y_tf32 + off) =
+                        make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
+                    *reinterpret_cast<float4 *>(p.y_tf32 + off + 4) =
+                        make_float4(round_tf32(v[4]), round_tf32(v[5]), round_tf32(v[6]), round_tf32(v[7]));
+                }
+                if (round_y) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = round_tf32(v[c]);
+                }
                 *reinterpret_cast<float4 *>(p.y + off) = make_float4(v[0], v[1], v[2], v[3]);
                 *reinterpret_cast<float4 *>(p.y + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
             } else {
@@ -175,7 +191,8 @@ conv_ffma_kernel(l3c_conv_t p, int Ho, int Wo, int tiles_x, int pad) {
                     if (co0 + c < p.Cout) {
                         float o = v[c];
                         if (p.residual) o += __ldg(p.residual + off + c);
-                        p.y[off + c] = o;
+                        if (p.y_tf32) p.y_tf32[off + c] = round_tf32(o);
+                        p.y[off + c] = round_y ? round_tf32(o) : o;
                     }
                 }
             }
@@ -191,7 +208,8 @@ conv_ffma_kernel(l3c_conv_t p, int Ho, int Wo, int tiles_x, int pad) {
                                    p.y_coff + cq;
                 float o = v[c];
                 if (p.residual) o += __ldg(p.residual + off);
-                p.y[off] = o;
+                if (p.y_tf32) p.y_tf32[off] = round_tf32(o);
+                p.y[off] = round_y ? round_tf32(o) : o;
             }
         }
     }

@@ -18,9 +18,12 @@
 // Accumulation order per output element is fixed (tap, K-half, k-step), independent of batch,
 // image size and tile position: encoder-side and decoder-side evaluations are bit-identical.
 //
-// Precision modes: L3C_PREC_TF32 feeds fp32 activations/weights straight to kind::tf32 (the tensor
-// core reads the upper 19 bits), fp32 accumulate.  (3xTF32 / bf16 are not built yet: the dispatcher
-// says so loudly.)
+// Precision: L3C_PREC_TF32.  The tensor core reads only the upper 19 bits of each fp32 operand
+// (truncation), which measurably biases the bit cost (+7e-4 bpsp at 512^2).  Operands are therefore
+// pre-rounded to TF32 with round-to-nearest: weights once on the host side, activations by the
+// producing layer's epilogue, which writes a second, rounded copy (`y_tf32`) next to the fp32 tensor
+// that residual adds and the fp32 layers keep using.  Accumulation is fp32 in TMEM.
+// (3xTF32 / bf16 are not built yet: the dispatcher says so loudly.)
 #include <cuda.h>
 
 #include "common.cuh"
@@ -127,10 +130,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 // instruction descriptor: D=f32, A=B=tf32, both K-major, N=64, M=128
 constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
+__device__ __forceinline__ float round_tf32(float x) {      // round-to-nearest TF32 image of x
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
 struct Params {
     const float *bias;      // padded to cout_pad
     const float *residual;
     float *y;
+    float *y_tf32;
     int N, H, W;
     int Cout, y_pitch, y_coff;
     int dilation;
@@ -248,6 +258,7 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         uint32_t acc = 0, acc_phase = 0;
         const bool relu = (p.flags & L3C_CONV_RELU) != 0;
         const bool shuffle = (p.flags & L3C_CONV_PIXEL_SHUFFLE2) != 0;
+        const bool round_y = (p.flags & L3C_CONV_ROUND_TF32) != 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             int q = t;
             const int ct = q % p.cout_tiles; q /= p.cout_tiles;
@@ -280,6 +291,17 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                                 v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
                             }
                         }
+                        if (p.y_tf32) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4)
+                                *reinterpret_cast<float4 *>(p.y_tf32 + off + i) =
+                                    make_float4(round_tf32(v[i]), round_tf32(v[i + 1]), round_tf32(v[i + 2]),
+                                                round_tf32(v[i + 3]));
+                        }
+                        if (round_y) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = round_tf32(v[i]);
+                        }
 #pragma unroll
                         for (int i = 0; i < 16; i += 4)
                             *reinterpret_cast<float4 *>(p.y + off + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -290,7 +312,9 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                         for (int i = 0; i < 16; ++i) {
                             const int co = co0 + i;
                             const int cq = co >> 2, si = (co >> 1) & 1, sj = co & 1;
-                            p.y[(((size_t)n * H2 + 2 * oy + si) * W2 + 2 * ox + sj) * p.y_pitch + p.y_coff + cq] = v[i];
+                            const size_t o2 = (((size_t)n * H2 + 2 * oy + si) * W2 + 2 * ox + sj) * p.y_pitch + p.y_coff + cq;
+                            if (p.y_tf32) p.y_tf32[o2] = round_tf32(v[i]);
+                            p.y[o2] = round_y ? round_tf32(v[i]) : v[i];
                         }
                     }
                 }
@@ -376,6 +400,7 @@ int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st) {
     q.bias = p.bias;
     q.residual = p.residual;
     q.y = p.y;
+    q.y_tf32 = p.y_tf32;
     q.N = p.N; q.H = p.H; q.W = p.W;
     q.Cout = p.Cout; q.y_pitch = p.y_pitch; q.y_coff = p.y_coff;
     q.dilation = p.dilation;

@@ -4,6 +4,7 @@ streams); every computation on the hot path is a kernel of libl3c_b200.so.
 Activation convention inside the package: NHWC fp32 contiguous tensors `[N, H, W, pitch]`.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -11,7 +12,8 @@ import torch
 from . import _lib
 from ._lib import lib, check, ConvDesc
 
-_PRECISION = {'mode': _lib.PREC_FP32}
+# default conv precision: env L3C_CONV_PRECISION (fp32 | tf32); see set_conv_precision
+_PRECISION = {'mode': _lib.PRECISIONS[os.environ.get('L3C_CONV_PRECISION', 'fp32')]}
 
 
 def set_conv_precision(name):
@@ -71,8 +73,29 @@ class PackedConv(object):
             w = self.conv.weight.detach().float()
             cout, cin, kh, kw = w.shape
             assert (cin, kh, kw) == (64, 3, 3)
+            w = round_to_tf32(w)
             self.w_tc = w.permute(2, 3, 0, 1).reshape(9, cout, 2, 32).permute(0, 2, 1, 3).contiguous()
         return self.w_tc, b
+
+
+def round_to_tf32(t):
+    """fp32 tensor -> nearest TF32-representable fp32 (10-bit mantissa, ties away from zero like
+    `cvt.rna.tf32.f32`).  Host-side preparation of the tensor-core weight image."""
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & -8192).view(torch.float32)
+
+
+class Act(object):
+    """An activation tensor (NHWC fp32) plus, in tensor-core mode, its TF32-rounded twin that the
+    next tcgen05 conv consumes (see conv_tcgen05.cu).  `r is f` when the tensor itself is rounded."""
+    __slots__ = ('f', 'r')
+
+    def __init__(self, f, r=None):
+        self.f, self.r = f, r
+
+
+def tensor_core_mode():
+    return _PRECISION['mode'] != _lib.PREC_FP32
 
 
 def _packed_obj(conv):
@@ -98,10 +121,16 @@ def tc_eligible(conv, x_pitch, y_pitch, y_coff):
 # conv stack
 # ----------------------------------------------------------------------------------------------
 def conv2d(conv, x, cin=None, relu=False, residual=None, pixel_shuffle=False, out=None, out_coff=0,
-           precision=None):
+           precision=None, want='plain'):
     """y = conv(x) [+ReLU] [+residual] on NHWC tensors, parameters taken from the nn.Conv2d `conv`
     (never called as a torch op).  `out`/`out_coff` write a channel slice of a wider NHWC buffer
-    (used for the atrous concat, prob_clf.py:71)."""
+    (used for the atrous concat, prob_clf.py:71).
+
+    x: tensor or Act.  want: 'plain' -> tensor; 'act' -> Act whose `.r` twin is produced when the
+    tensor-core mode is on; 'round' -> Act whose only tensor is TF32-rounded (for activations that
+    feed nothing but a following tensor-core conv)."""
+    xa = x if isinstance(x, Act) else Act(x)
+    x = xa.f
     require_cuda(x, 'x')
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
     N, H, W, xp = x.shape
@@ -118,21 +147,36 @@ def conv2d(conv, x, cin=None, relu=False, residual=None, pixel_shuffle=False, ou
             out = torch.empty(N, Ho * 2, Wo * 2, cout // 4, dtype=torch.float32, device=x.device)
         else:
             out = torch.empty(N, Ho, Wo, cout, dtype=torch.float32, device=x.device)
-    prec = _PRECISION['mode'] if precision is None else precision
-    if prec != _lib.PREC_FP32 and tc_eligible(conv, xp, out.shape[-1], out_coff) and cin == 64:
+    mode = _PRECISION['mode'] if precision is None else precision
+    prec = mode
+    x_in = x
+    if mode != _lib.PREC_FP32 and tc_eligible(conv, xp, out.shape[-1], out_coff) and cin == 64:
         w, b = _packed_obj(conv).get_tc()
+        if xa.r is not None:
+            x_in = xa.r                       # TF32-rounded operand image
     else:
         prec = _lib.PREC_FP32
         w, b = packed(conv)
-    d = ConvDesc(x=x.data_ptr(), w=w.data_ptr(), bias=b.data_ptr(),
+    out_r = None
+    if mode != _lib.PREC_FP32:
+        if want == 'act':
+            out_r = torch.empty_like(out)
+        elif want == 'round':
+            flags |= _lib.CONV_ROUND_TF32
+    d = ConvDesc(x=x_in.data_ptr(), w=w.data_ptr(), bias=b.data_ptr(),
                  residual=residual.data_ptr() if residual is not None else None, y=out.data_ptr(),
+                 y_tf32=out_r.data_ptr() if out_r is not None else None,
                  N=N, H=H, W=W, Cin=cin, x_pitch=xp, Cout=cout, cout_pad=b.shape[0],
                  y_pitch=out.shape[-1], y_coff=out_coff, ksize=kh, stride=stride, dilation=dil,
                  flags=flags, precision=prec)
     if residual is not None:
         assert residual.shape == out.shape and residual.is_contiguous()
     check(lib.l3c_conv2d(ctypes.byref(d), _stream_ptr()))
-    return out
+    if want == 'plain':
+        return out
+    if want == 'round':
+        return Act(out, out if mode != _lib.PREC_FP32 else None)
+    return Act(out, out_r)
 
 
 def rgb_prep(img_u8, conv1, conv2):

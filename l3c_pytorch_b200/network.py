@@ -79,16 +79,19 @@ class ResBlock(nn.Module):
                                   conv(n_feats, n_feats, kernel_size))
 
     def forward(self, x):
-        r = E.conv2d(self.body[0], x, relu=True)
-        return E.conv2d(self.body[2], r, residual=x)             # res += x
+        """x: engine.Act.  The intermediate only feeds the second conv -> TF32-rounded in place when
+        the tensor cores are on; the block output feeds the next conv AND a residual add -> both."""
+        r = E.conv2d(self.body[0], x, relu=True, want='round')
+        return E.conv2d(self.body[2], r, residual=x.f, want='act')           # res += x
 
 
 def _run_body(body, x):
-    """Sequential of ResBlocks + final conv, plus the outer skip `body(x) + x` (net.py:144,181)."""
+    """Sequential of ResBlocks + final conv, plus the outer skip `body(x) + x` (net.py:144,181).
+    x and the result are engine.Act."""
     y = x
     for m in list(body)[:-1]:
         y = m(y)
-    return E.conv2d(body[-1], y, residual=x)
+    return E.conv2d(body[-1], y, residual=x.f, want='act')
 
 
 class Upsampler(nn.Sequential):
@@ -99,7 +102,7 @@ class Upsampler(nn.Sequential):
         super(Upsampler, self).__init__(conv(n_feats, 4 * n_feats, 3, True), nn.PixelShuffle(2))
 
     def forward(self, x):
-        return E.conv2d(self[0], x, pixel_shuffle=True)
+        return E.conv2d(self[0], x, pixel_shuffle=True, want='act')
 
 
 class Head(nn.Module):
@@ -158,9 +161,9 @@ class EDSRLikeEnc(nn.Module):
         self.q = Quantizer(self.levels, config_ms.q.sigma)
 
     def forward(self, x):
-        x = E.conv2d(self.down, x)
-        F = _run_body(self.body, x)
-        sym, bnq = E.quantize_head(F, self.to_q[0], self.levels)
+        x = E.conv2d(self.down, x, want='act')
+        F = _run_body(self.body, x)                                # engine.Act
+        sym, bnq = E.quantize_head(F.f, self.to_q[0], self.levels)
         return EncOut(bnq, bnq, sym, self.L, F)
 
 
@@ -199,10 +202,11 @@ class EDSRDec(nn.Module):
         self.tail = Upsampler(conv, 2, Cf)
 
     def forward(self, bn8, features_to_fuse=None):
-        """bn8: NHWC [N,h,w,8] (q.C channels used)."""
-        x = E.conv2d(self.head, bn8, residual=features_to_fuse)       # head(x) + F_prev
+        """bn8: NHWC [N,h,w,8] (q.C channels used); features_to_fuse: engine.Act or tensor or None."""
+        fuse = features_to_fuse.f if isinstance(features_to_fuse, E.Act) else features_to_fuse
+        x = E.conv2d(self.head, bn8, residual=fuse, want='act')       # head(x) + F_prev
         x = _run_body(self.body, x)
-        return DecOut(self.tail(x))
+        return DecOut(self.tail(x))                                   # engine.Act
 
 
 class Net(nn.Module):
@@ -226,8 +230,9 @@ class StackedAtrousConvs(nn.Module):
         self.lin = conv(len(rates) * Cin, Cout, 1, bias=bias)
 
     def forward(self, x):
-        N, H, W, Cin = x.shape
-        cat = torch.empty(N, H, W, Cin * len(self.atrous), dtype=torch.float32, device=x.device)
+        """x: engine.Act -> NHWC parameter tensor."""
+        N, H, W, Cin = x.f.shape
+        cat = torch.empty(N, H, W, Cin * len(self.atrous), dtype=torch.float32, device=x.f.device)
         for i, a in enumerate(self.atrous):
             E.conv2d(a, x, out=cat, out_coff=i * Cin)                 # concat by channel slice
         return E.conv2d(self.lin, cat)
@@ -384,6 +389,7 @@ class MultiscaleNetwork(nn.Module):
         return out
 
     def get_P_nhwc(self, scale, bn8, dec_F_prev=None):
+        """-> (parameters NHWC, decoder features as engine.Act for the next finer scale)."""
         assert 0 <= scale < self.config_ms.num_scales, 'Out of range: {}'.format(scale)
         F = self.nets[scale].dec(bn8, dec_F_prev).F
         return self.prob_clfs[scale](F), F
@@ -393,4 +399,4 @@ class MultiscaleNetwork(nn.Module):
         bn8 = to_nhwc(bn_q, 8)
         Fp = None if dec_F_prev is None else to_nhwc(dec_F_prev)
         l, F = self.get_P_nhwc(scale, bn8, Fp)
-        return nchw_view(l), nchw_view(F)
+        return nchw_view(l), nchw_view(F.f)

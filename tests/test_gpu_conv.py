@@ -135,3 +135,29 @@ def test_bicubic_matches_pillow():
             w, h = pil.size
             want = torch.from_numpy(np.array(pil.resize((int(w * 0.5), int(h * 0.5)), Image.BICUBIC))).permute(2, 0, 1)
             assert torch.equal(got[n], want), (H, W, n, (got[n].int() - want.int()).abs().max())
+
+
+@pytest.mark.parametrize('cout,rate,H,W,kw', [(64, 1, 16, 16, {}), (64, 2, 24, 40, {}), (64, 4, 19, 37, {}),
+                                              (256, 1, 12, 20, dict(pixel_shuffle=True)), (64, 1, 8, 16, dict(relu=True)),
+                                              (64, 1, 3, 5, {})])
+def test_tcgen05_conv_vs_torch_on_tf32_operands(cout, rate, H, W, kw):
+    """The tensor-core kernel (TMA + tcgen05.mma kind::tf32 + TMEM) against a PyTorch fp32 CPU conv
+    fed with the SAME TF32-rounded operands: products are exact, only the fp32 accumulation order
+    differs -> rtol 1e-4."""
+    from l3c_pytorch_b200 import engine as E, _lib
+    conv = _conv_module(64, cout, 3, 1, rate)
+    x = torch.randn(2, 64, H, W)
+    xr = E.round_to_tf32(x)
+    wr = E.round_to_tf32(conv.weight.detach())
+    want = F.conv2d(xr, wr, conv.bias.detach(), padding=rate, dilation=rate)
+    if kw.get('relu'):
+        want = F.relu(want)
+    if kw.get('pixel_shuffle'):
+        want = F.pixel_shuffle(want, 2)
+    xa = E.Act(_nhwc(x), _nhwc(xr))
+    got = E.conv2d(conv.cuda(), xa, precision=_lib.PREC_TF32, want='act', **kw)
+    np.testing.assert_allclose(got.f.cpu().permute(0, 3, 1, 2).numpy(), want.numpy(), rtol=1e-4, atol=1e-4)
+    # the twin written by the epilogue is the RN-TF32 image of the fp32 result
+    assert torch.equal(got.r.cpu(), E.round_to_tf32(got.f.cpu()))
+    r_only = E.conv2d(conv.cuda(), xa, precision=_lib.PREC_TF32, want='round', **kw)
+    assert torch.equal(r_only.f.cpu(), got.r.cpu())
