@@ -204,6 +204,19 @@ def run_ours(args):
     sizes = info['sizes']
     counts = l3c_dist.gather_byte_counts(sizes, n_global, rank, world)       # the one collective (NCCL)
     bpsp = l3c_dist.global_bpsp(counts, 3 * HW * HW)
+    # parity with the reference's own torchac path on the same weights/image (golden: image seed 1000)
+    parity = None
+    try:
+        with open(os.path.join(ROOT, 'tests', 'golden', 'summary.json')) as f:
+            ref0 = json.load(f)['l3c_512x512_i0']
+        if rank == 0 and (max(args.warmup, 1) - 1) % n_sets == 0 or n_sets == 1:
+            pass
+        d0, _ = codec.encode_batch(dev_sets[0][:1])
+        if rank == 0:
+            parity = {'image': 'seed 1000, 3x512x512', 'bytes': len(d0[0]), 'reference_bytes': ref0['ref_bytes'],
+                      'abs_dbpsp': abs(len(d0[0]) - ref0['ref_bytes']) * 8 / (3.0 * HW * HW)}
+    except (OSError, KeyError):
+        pass
 
     # ---- timed: device-resident
     sampler = ClockSampler(local_rank)
@@ -297,7 +310,7 @@ def run_ours(args):
                                                                 'collective' % world,
                        'conv_precision': args.precision,
                        'l2': 'working set >> L2 (1 GB of activations per layer), inputs alternate between batches'},
-            'bpsp': bpsp,
+            'bpsp': bpsp, 'bpsp_parity': parity,
             'e2e': {'value': e2e_value, 'unit': 'Mpixels/s', 'h2d_bytes_per_step': img_bytes + cont_bytes,
                     'd2h_bytes_per_step': cont_bytes + img_bytes},
             'gpu_launches': None,
@@ -333,7 +346,7 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('L3C_CONV_PRECISION', 'fp32'),
+    ap.add_argument('--precision', default=os.environ.get('L3C_CONV_PRECISION', 'tf32'),
                     choices=['fp32', 'tf32', 'tf32x3', 'bf16'])
     ap.add_argument('--images-per-gpu', type=int, default=IMAGES_PER_GPU)
     ap.add_argument('--no-cpu-baseline', action='store_true')

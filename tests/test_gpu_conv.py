@@ -10,6 +10,7 @@ from tests import util
 
 pytestmark = pytest.mark.gpu
 RTOL, ATOL = 2e-5, 2e-5
+FP32 = 0      # _lib.PREC_FP32: these tests pin the CUDA-core path whatever the session default is
 
 
 def _conv_module(cin, cout, k, stride=1, rate=1, seed=0):
@@ -31,7 +32,7 @@ def test_conv_vs_torch(cin, cout, k, stride, rate, H, W):
     conv = _conv_module(cin, cout, k, stride, rate)
     x = torch.randn(2, cin, H, W)
     want = conv(x).detach()
-    got = E.conv2d(conv.cuda(), _nhwc(x)).cpu().permute(0, 3, 1, 2)
+    got = E.conv2d(conv.cuda(), _nhwc(x), precision=FP32).cpu().permute(0, 3, 1, 2)
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=RTOL, atol=ATOL)
 
 
@@ -40,13 +41,13 @@ def test_conv_epilogues():
     conv = _conv_module(64, 64, 3)
     x, r = torch.randn(2, 64, 20, 28), torch.randn(2, 64, 20, 28)
     cc = conv.cuda()
-    got = E.conv2d(cc, _nhwc(x), relu=True).cpu().permute(0, 3, 1, 2)
+    got = E.conv2d(cc, _nhwc(x), relu=True, precision=FP32).cpu().permute(0, 3, 1, 2)
     np.testing.assert_allclose(got.numpy(), F.relu(conv.cpu()(x)).detach().numpy(), rtol=RTOL, atol=ATOL)
-    got = E.conv2d(cc.cuda(), _nhwc(x), residual=_nhwc(r)).cpu().permute(0, 3, 1, 2)
+    got = E.conv2d(cc.cuda(), _nhwc(x), residual=_nhwc(r), precision=FP32).cpu().permute(0, 3, 1, 2)
     np.testing.assert_allclose(got.numpy(), (conv.cpu()(x) + r).detach().numpy(), rtol=RTOL, atol=ATOL)
     # channel-slice output (atrous concat)
     buf = torch.zeros(2, 20, 28, 192).cuda()
-    E.conv2d(conv.cuda(), _nhwc(x), out=buf, out_coff=64)
+    E.conv2d(conv.cuda(), _nhwc(x), out=buf, out_coff=64, precision=FP32)
     b = buf.cpu()
     assert (b[..., :64] == 0).all() and (b[..., 128:] == 0).all()
     np.testing.assert_allclose(b[..., 64:128].permute(0, 3, 1, 2).numpy(), conv.cpu()(x).detach().numpy(),
@@ -54,7 +55,7 @@ def test_conv_epilogues():
     # pixel shuffle
     up = _conv_module(64, 256, 3, seed=3)
     want = F.pixel_shuffle(up(x), 2).detach()
-    got = E.conv2d(up.cuda(), _nhwc(x), pixel_shuffle=True).cpu().permute(0, 3, 1, 2)
+    got = E.conv2d(up.cuda(), _nhwc(x), pixel_shuffle=True, precision=FP32).cpu().permute(0, 3, 1, 2)
     assert got.shape == want.shape
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=RTOL, atol=ATOL)
 
@@ -66,27 +67,28 @@ def test_small_channel_convs_and_padding_lanes():
     x = torch.randn(1, 3, 17, 23)
     x4 = torch.zeros(1, 17, 23, 4)
     x4[..., :3] = x.permute(0, 2, 3, 1)
-    got = E.conv2d(head.cuda(), x4.cuda(), cin=3).cpu().permute(0, 3, 1, 2)
+    got = E.conv2d(head.cuda(), x4.cuda(), cin=3, precision=FP32).cpu().permute(0, 3, 1, 2)
     np.testing.assert_allclose(got.numpy(), head.cpu()(x).detach().numpy(), rtol=RTOL, atol=ATOL)
     dh = _conv_module(5, 64, 1, seed=2)
     b = torch.randn(2, 5, 9, 11)
     b8 = torch.zeros(2, 9, 11, 8)
     b8[..., :5] = b.permute(0, 2, 3, 1)
     fuse = torch.randn(2, 64, 9, 11)
-    got = E.conv2d(dh.cuda(), b8.cuda(), residual=_nhwc(fuse)).cpu().permute(0, 3, 1, 2)
+    got = E.conv2d(dh.cuda(), b8.cuda(), residual=_nhwc(fuse), precision=FP32).cpu().permute(0, 3, 1, 2)
     np.testing.assert_allclose(got.numpy(), (dh.cpu()(b) + fuse).detach().numpy(), rtol=RTOL, atol=ATOL)
 
 
-def test_conv_independent_of_batch_and_position():
+@pytest.mark.parametrize('prec', [0, 1])
+def test_conv_independent_of_batch_and_position(prec):
     """enc/dec bit-exactness: the same pixel neighbourhood gives the same bits whatever the batch
-    size, image size or tile it lands in."""
+    size, image size or tile it lands in -- for the CUDA-core and the tensor-core kernel."""
     from l3c_pytorch_b200 import engine as E
     conv = _conv_module(64, 64, 3).cuda()
     x = torch.randn(3, 64, 40, 56)
-    full = E.conv2d(conv, _nhwc(x)).cpu()
-    one = E.conv2d(conv, _nhwc(x[1:2])).cpu()
+    full = E.conv2d(conv, _nhwc(x), precision=prec).cpu()
+    one = E.conv2d(conv, _nhwc(x[1:2]), precision=prec).cpu()
     assert torch.equal(full[1:2], one)
-    crop = E.conv2d(conv, _nhwc(x[:, :, 8:32, 16:48])).cpu()
+    crop = E.conv2d(conv, _nhwc(x[:, :, 8:32, 16:48]), precision=prec).cpu()
     assert torch.equal(full[:, 9:31, 17:47], crop[:, 1:-1, 1:-1])
 
 
