@@ -229,6 +229,55 @@ class BatchCodec(object):
             return S.cpu(), pads
         return S, pads
 
+    def _decode_rgb_pipelined(self, l, S, tg, C, K, L, table, d, dev, n_chunks=16):
+        """RGB scale: channel c's means depend on the decoded channels < c at the same pixel
+        (logistic_mixture.py:262-272), so the reference codes R, G, B strictly one after the other.
+        Here the three serial decoders run concurrently, staggered by one chunk of pixels: as soon as
+        chunk j of channel c-1 is decoded, the CDF rows of chunk j of channel c are built (whole GPU,
+        short) and channel c's warps continue -- coder state is carried across launches.  Serial
+        depth drops from 3*HW to (1 + 2/n_chunks)*HW symbols."""
+        N, HW = S.shape[0], S.shape[2] * S.shape[3]
+        csz = max(2048, -(-HW // n_chunks))
+        csz = -(-csz // 64) * 64
+        chunks = [(p0, min(csz, HW - p0)) for p0 in range(0, HW, csz)]
+        state = torch.zeros(N * C * 4, dtype=torch.int32, device=dev)
+        d['state'][:] = state.data_ptr() + 16 * (np.arange(N)[:, None] * C + np.arange(C)[None, :])
+        descs = [E._desc_to_device(np.ascontiguousarray(d[:, c]), dev) for c in range(C)]
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, '_streams'):
+            self._streams = [[torch.cuda.Stream(device=dev) for _ in range(3)] for _ in range(2)]
+        s_bld, s_dec = self._streams
+        start = torch.cuda.Event()
+        start.record(cur)
+        for st in s_bld[:C] + s_dec[:C]:
+            st.wait_event(start)
+        prev_dec = None
+        last = []
+        for (p0, npx) in chunks:
+            this_dec = []
+            for c in range(C):
+                with torch.cuda.stream(s_bld[c]):
+                    if c > 0:
+                        s_bld[c].wait_event(this_dec[c - 1])
+                    E.dmll_build_table(l, S, tg, C, K, L, True, c, table, pix0=p0, npix=npx)
+                    eb = torch.cuda.Event()
+                    eb.record(s_bld[c])
+                with torch.cuda.stream(s_dec[c]):
+                    s_dec[c].wait_event(eb)
+                    E.ac_decode_streams(None, dev, L, first=p0, count=npx, desc_dev=descs[c], n=N)
+                    ed = torch.cuda.Event()
+                    ed.record(s_dec[c])
+                this_dec.append(ed)
+            prev_dec = this_dec
+            last = this_dec
+        for ev in last:
+            cur.wait_event(ev)
+        for st in s_bld[:C]:
+            e = torch.cuda.Event()
+            e.record(st)
+            cur.wait_event(e)
+        del prev_dec
+
     def decode_device(self, blob, offs, lens, shapes):
         """Decode streams that already sit in HBM: `blob` uint8 device buffer (readable 4 bytes past
         every stream), offs/lens int64 [N][streams per image] in container order (coarse -> fine,
@@ -265,11 +314,7 @@ class BatchCodec(object):
                 d['row_pitch'][:] = pitch
                 tg = dmll.targets(dev)
                 if dmll.rgb_scale:
-                    # channel c's means depend on the decoded channels < c at the same pixel
-                    # (logistic_mixture.py:262-272): build rows, then decode, channel by channel
-                    for c in range(C):
-                        E.dmll_build_table(l, S, tg, C, K, dmll.L, True, c, table)
-                        E.ac_decode_streams(np.ascontiguousarray(d[:, c]), dev, dmll.L)
+                    self._decode_rgb_pipelined(l, S, tg, C, K, dmll.L, table, d, dev)
                 else:
                     E.dmll_build_table(l, S, tg, C, K, dmll.L, False, -1, table)
                     E.ac_decode_streams(desc, dev, dmll.L)

@@ -310,10 +310,13 @@ def pack_streams(desc_dev, lens_dev, dst_off_np, n, blob):
     check(lib.l3c_pack_streams(_ptr(desc_dev), _ptr(lens_dev), _ptr(off), n, _ptr(blob), _stream_ptr()))
 
 
-def ac_decode_streams(desc_np, device, L, first=0, count=None, desc_dev=None):
-    n = desc_np.shape[0]
+def ac_decode_streams(desc_np, device, L, first=0, count=None, desc_dev=None, n=None):
+    """Decode symbols [first, first+count) of every stream.  Pass `desc_dev` (+ `n`) to reuse an
+    uploaded descriptor array across chunked launches."""
     if desc_dev is None:
         desc_dev = _desc_to_device(desc_np, device)
+    if n is None:
+        n = desc_np.shape[0]
     if count is None:
         count = int(desc_np['n_sym'].max()) if n else 0
     check(lib.l3c_ac_decode_streams(_ptr(desc_dev), n, L, first, count, _stream_ptr()))
