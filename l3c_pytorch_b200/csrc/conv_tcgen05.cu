@@ -146,6 +146,9 @@ struct Params {
     int dilation;
     unsigned flags;
     int tiles_x, tiles_y, cout_tiles, total_tiles;
+    int taps;        // 9 (3x3) or 1 (1x1)
+    int kpairs;      // Cin / 64: stage iterations per tap, each stage = 2 K-halves of 32 channels
+    int cout_rows;   // rows per (tap, K-half) slab of the weight image = cout_tiles * 64
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -198,18 +201,20 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             const int tx = q % p.tiles_x; q /= p.tiles_x;
             const int ty = q % p.tiles_y; q /= p.tiles_y;
             const int n = q;
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int it = 0; it < p.taps * p.kpairs; ++it) {
+                const int tap = it / p.kpairs, kp = it % p.kpairs;
                 if (lane == 0) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     mbar_expect_tx(full_bar(stage), STAGE_BYTES);
                     const uint32_t a0 = smem_base + stage * STAGE_BYTES;
-                    const int x0 = tx * TW + (tap % 3 - 1) * d;
-                    const int y0 = ty * TH + (tap / 3 - 1) * d;
-                    tma_load_4d(a0, &map_x, full_bar(stage), 0, x0, y0, n);
-                    tma_load_4d(a0 + A_HALF, &map_x, full_bar(stage), 32, x0, y0, n);
-                    const int wrow = (tap * 2) * p.cout_tiles * 64 + ct * 64;   // rows: [tap][khalf][cout]
+                    const int x0 = tx * TW + (p.taps == 9 ? (tap % 3 - 1) * d : 0);
+                    const int y0 = ty * TH + (p.taps == 9 ? (tap / 3 - 1) * d : 0);
+                    tma_load_4d(a0, &map_x, full_bar(stage), kp * 64, x0, y0, n);
+                    tma_load_4d(a0 + A_HALF, &map_x, full_bar(stage), kp * 64 + 32, x0, y0, n);
+                    // weight image rows: [tap][K-half][cout_rows]
+                    const int wrow = (tap * 2 * p.kpairs + 2 * kp) * p.cout_rows + ct * 64;
                     tma_load_2d(a0 + 2 * A_HALF, &map_w, full_bar(stage), 0, wrow);
-                    tma_load_2d(a0 + 2 * A_HALF + B_HALF, &map_w, full_bar(stage), 0, wrow + p.cout_tiles * 64);
+                    tma_load_2d(a0 + 2 * A_HALF + B_HALF, &map_w, full_bar(stage), 0, wrow + p.cout_rows);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -226,7 +231,8 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             }
             __syncwarp();
             const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-            for (int tap = 0; tap < 9; ++tap) {
+            const int n_it = p.taps * p.kpairs;
+            for (int it = 0; it < n_it; ++it) {
                 if (lane == 0) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
@@ -239,11 +245,11 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                         for (int k = 0; k < 4; ++k) {
                             // +32 B (8 tf32) along K inside the 128 B swizzle row: +2 in 16-byte units
                             mma_tf32(d_tmem, da + 2u * k, db + 2u * k, IDESC_TF32,
-                                     (tap | kh | k) != 0 ? 1u : 0u);
+                                     (it | kh | k) != 0 ? 1u : 0u);
                         }
                     }
                     mma_commit(empty_bar(stage));                 // frees the smem slot when the MMAs retire
-                    if (tap == 8) mma_commit(tfull_bar(acc));     // accumulator complete -> epilogue
+                    if (it == n_it - 1) mma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -275,36 +281,49 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             for (int c0 = 0; c0 < 64; c0 += 16) {
                 float v[16];
                 tmem_ld16(taddr + c0, v);
-                if (inside) {
-                    const int co0 = ct * 64 + c0;
+                const int co0 = ct * 64 + c0;
+                if (inside && co0 < p.Cout) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        v[i] += __ldg(p.bias + co0 + i);
+                        v[i] += __ldg(p.bias + co0 + i);          // bias is padded to cout_rows
                         if (relu) v[i] = fmaxf(v[i], 0.f);
                     }
                     if (!shuffle) {
                         const size_t off = (((size_t)n * p.H + oy) * p.W + ox) * p.y_pitch + p.y_coff + co0;
-                        if (p.residual) {
+                        const bool vec = (((p.y_pitch | p.y_coff) & 3) == 0) && (co0 + 16 <= p.Cout);
+                        if (vec) {
+                            if (p.residual) {
 #pragma unroll
-                            for (int i = 0; i < 16; i += 4) {
-                                const float4 r = __ldg(reinterpret_cast<const float4 *>(p.residual + off + i));
-                                v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
+                                for (int i = 0; i < 16; i += 4) {
+                                    const float4 r = __ldg(reinterpret_cast<const float4 *>(p.residual + off + i));
+                                    v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
+                                }
                             }
-                        }
-                        if (p.y_tf32) {
+                            if (p.y_tf32) {
+#pragma unroll
+                                for (int i = 0; i < 16; i += 4)
+                                    *reinterpret_cast<float4 *>(p.y_tf32 + off + i) =
+                                        make_float4(round_tf32(v[i]), round_tf32(v[i + 1]), round_tf32(v[i + 2]),
+                                                    round_tf32(v[i + 3]));
+                            }
+                            if (round_y) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = round_tf32(v[i]);
+                            }
 #pragma unroll
                             for (int i = 0; i < 16; i += 4)
-                                *reinterpret_cast<float4 *>(p.y_tf32 + off + i) =
-                                    make_float4(round_tf32(v[i]), round_tf32(v[i + 1]), round_tf32(v[i + 2]),
-                                                round_tf32(v[i + 3]));
-                        }
-                        if (round_y) {
+                                *reinterpret_cast<float4 *>(p.y + off + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        } else {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = round_tf32(v[i]);
+                            for (int i = 0; i < 16; ++i) {
+                                if (co0 + i < p.Cout) {
+                                    float o = v[i];
+                                    if (p.residual) o += __ldg(p.residual + off + i);
+                                    if (p.y_tf32) p.y_tf32[off + i] = round_tf32(o);
+                                    p.y[off + i] = round_y ? round_tf32(o) : o;
+                                }
+                            }
                         }
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4 *>(p.y + off + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                     } else {
                         // out[n, 2*oy+i, 2*ox+j, cq] = conv[n, oy, ox, 4*cq + 2*i + j]
                         const int H2 = p.H * 2, W2 = p.W * 2;
@@ -364,17 +383,21 @@ int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st) {
     // The tensor-core kernel covers the 3x3 / 64-input-channel layers (> 92 % of the FLOPs of a round
     // trip).  The host mirror routes the other layers (5x5/s2 down-sampling, 1x1 convs, Cin != 64) to
     // L3C_PREC_FP32 explicitly (engine.conv2d); nothing falls back silently here.
-    const bool eligible = p.ksize == 3 && p.stride == 1 && p.Cin == 64 && p.x_pitch == 64 && p.Cout % 64 == 0 &&
-                          (p.y_pitch % 4 == 0) && (p.y_coff % 4 == 0);
-    L3C_REQUIRE(eligible, "l3c_conv2d: tcgen05 path needs ksize=3 stride=1 Cin=x_pitch=64 Cout%%64==0 "
+    const bool k3 = p.ksize == 3 && p.stride == 1 && p.Cin == 64 && p.x_pitch == 64;
+    const bool k1 = p.ksize == 1 && p.stride == 1 && p.Cin % 64 == 0 && p.x_pitch == p.Cin &&
+                    !(p.flags & L3C_CONV_PIXEL_SHUFFLE2);
+    const bool eligible = (k3 || k1) && p.cout_pad % 64 == 0 && p.cout_pad >= p.Cout &&
+                          (k1 || ((p.Cout % 64 == 0) && (p.y_pitch % 4 == 0) && (p.y_coff % 4 == 0)));
+    L3C_REQUIRE(eligible, "l3c_conv2d: tcgen05 path needs 3x3/Cin=64 or 1x1/Cin%%64==0, stride 1 "
                           "(got k=%d s=%d Cin=%d pitch=%d Cout=%d)", p.ksize, p.stride, p.Cin, p.x_pitch, p.Cout);
-
+    const int taps = k3 ? 9 : 1;
+    const int kpairs = p.Cin / 64;
     EncodeTiledFn encode = get_encode_fn();
     L3C_REQUIRE(encode != nullptr, "l3c_conv2d: cuTensorMapEncodeTiled is not available from the driver");
 
     alignas(64) CUtensorMap map_x, map_w;
     {
-        cuuint64_t dims[4] = {64, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+        cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
         cuuint64_t strides[3] = {(cuuint64_t)p.x_pitch * 4, (cuuint64_t)p.W * p.x_pitch * 4,
                                  (cuuint64_t)p.H * p.W * p.x_pitch * 4};
         cuuint32_t box[4] = {32, TW, TH, 1};
@@ -384,10 +407,10 @@ int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st) {
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         L3C_REQUIRE(r == CUDA_SUCCESS, "l3c_conv2d: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
     }
-    const int cout_tiles = p.Cout / 64;
+    const int cout_tiles = p.cout_pad / 64;
     {
-        // tensor-core weight image: [tap 9][K-half 2][Cout][32] fp32 (see engine.PackedConv.get_tc)
-        cuuint64_t dims[2] = {32, (cuuint64_t)(9 * 2 * p.Cout)};
+        // tensor-core weight image: [tap][K-half = Cin/32][cout_pad][32] fp32 (engine.PackedConv.get_tc)
+        cuuint64_t dims[2] = {32, (cuuint64_t)taps * 2 * kpairs * p.cout_pad};
         cuuint64_t strides[1] = {128};
         cuuint32_t box[2] = {32, 64};
         cuuint32_t estr[2] = {1, 1};
@@ -408,6 +431,9 @@ int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st) {
     q.tiles_x = ceil_div(p.W, TW);
     q.tiles_y = ceil_div(p.H, TH);
     q.cout_tiles = cout_tiles;
+    q.taps = taps;
+    q.kpairs = kpairs;
+    q.cout_rows = p.cout_pad;
     q.total_tiles = p.N * q.tiles_x * q.tiles_y * cout_tiles;
 
     static int n_sm = 0;

@@ -133,85 +133,63 @@ ac_encode_kernel(const l3c_enc_stream_t *__restrict__ streams, int n_streams,
 // ---------------------------------------------------------------------------------------------
 // decoder
 // ---------------------------------------------------------------------------------------------
-struct BitSource {
-    const uint32_t *base;  // 4-byte aligned address at or below the first code byte
-    uint32_t mis;          // stream start = (const uint8_t*)base + mis, mis in [0,3]
-    uint32_t in_len;       // bytes; everything past it reads as zero (torchac.cpp:109-112)
-    uint32_t wnext;        // index of the word held in `ahead`
-    uint32_t ahead;        // prefetched word (already big-endian -> native)
-    uint64_t win;          // upcoming bits, left aligned
-    int navail;            // valid bits in win, kept >= 32
-    uint32_t consumed;     // total bits taken (saved as coder state)
+__device__ __forceinline__ uint32_t shl_c(uint32_t x, uint32_t n) {   // x << n, 0 for n >= 32 (PTX clamps)
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+    return r;
+}
+__device__ __forceinline__ uint32_t shr_c(uint32_t x, uint32_t n) {   // x >> n, 0 for n >= 32
+    uint32_t r;
+    asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+    return r;
+}
 
-    __device__ __forceinline__ void open(const uint8_t *in, uint32_t len) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(in);
-        mis = (uint32_t)(a & 3u);
-        base = reinterpret_cast<const uint32_t *>(a - mis);
-        in_len = len;
-    }
-    // 32 code bits starting at byte 4*i of the stream, MSB first; streams may start at any byte
-    // address (they are decoded in place from the container), so two aligned words are funnelled.
+// MSB-first bit reader over a byte stream that may start at ANY address (streams are decoded in
+// place from the container): words are fetched from the 4-byte aligned address below the stream and
+// the first `8*mis` bits are simply skipped; bytes past the end read as zero (torchac.cpp:109-112).
+struct BitSource {
+    const uint32_t *base;
+    uint32_t end_byte;     // mis + in_len: first byte (relative to base) that is past the stream
+    uint32_t wbase;        // word index of the upper half of `win`
+    uint64_t win;          // words wbase, wbase+1
+    uint32_t nextw;        // word wbase+2, prefetched
+    uint32_t pos;          // next unread bit, relative to base; invariant 0 <= pos - 32*wbase < 32
+
     __device__ __forceinline__ uint32_t word(uint32_t i) const {
-        const uint32_t b = 4u * i;
-        if (b >= in_len) return 0u;
-        const uint32_t a0 = __ldg(base + i);
-        const uint32_t a1 = (mis != 0u) ? __ldg(base + i + 1) : 0u;
-        const uint32_t raw = __funnelshift_r(a0, a1, 8u * mis);      // little-endian bytes b..b+3
-        uint32_t w = __byte_perm(raw, 0, 0x0123);
-        const uint32_t rem = in_len - b;
-        if (rem < 4u) w &= 0xFFFFFFFFu << (8u * (4u - rem));
+        const int rem = (int)end_byte - (int)(4u * i);
+        if (rem <= 0) return 0u;
+        uint32_t w = __byte_perm(__ldg(base + i), 0, 0x0123);
+        if (rem < 4) w &= 0xFFFFFFFFu << (8 * (4 - rem));
         return w;
     }
-    __device__ __forceinline__ void seek(uint32_t bitpos) {
-        const uint32_t w = bitpos >> 5;
-        const int off = (int)(bitpos & 31u);
-        win = (((uint64_t)word(w) << 32) | (uint64_t)word(w + 1)) << off;
-        navail = 64 - off;
-        wnext = w + 2;
-        ahead = word(wnext);
-        consumed = bitpos;
-        refill();
+    __device__ __forceinline__ uint32_t open(const uint8_t *in, uint32_t len) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(in);
+        const uint32_t mis = (uint32_t)(a & 3u);
+        base = reinterpret_cast<const uint32_t *>(a - mis);
+        end_byte = mis + len;
+        return 8u * mis;                                   // bit position of the first code bit
     }
-    __device__ __forceinline__ void refill() {
-        if (navail < 32) {
-            win |= (uint64_t)ahead << (32 - navail);
-            navail += 32;
-            wnext++;
-            ahead = word(wnext);
+    __device__ __forceinline__ void seek(uint32_t p) {
+        wbase = p >> 5;
+        win = ((uint64_t)word(wbase) << 32) | (uint64_t)word(wbase + 1);
+        nextw = word(wbase + 2);
+        pos = p;
+    }
+    // the next 32 bits (not consumed)
+    __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)((win << (pos & 31u)) >> 32); }
+    __device__ __forceinline__ void skip(uint32_t n) {     // n <= 32
+        pos += n;
+        if ((pos >> 5) != wbase) {
+            win = (win << 32) | (uint64_t)nextw;
+            wbase++;
+            nextw = word(wbase + 2);
         }
     }
-    __device__ __forceinline__ uint32_t take(int n) {        // 1 <= n <= 32
-        const uint32_t v = (uint32_t)(win >> (64 - n));
-        win <<= n;
-        navail -= n;
-        consumed += (uint32_t)n;
-        refill();
+    __device__ __forceinline__ uint32_t take(uint32_t n) { // n <= 32; take(0) == 0
+        const uint32_t v = shr_c(peek32(), 32u - n);
+        skip(n);
         return v;
     }
-};
-
-template <int EPL, bool FULLROW>
-struct RowRegs;
-template <bool FULLROW>
-struct RowRegs<8, FULLROW> {
-    uint4 v;
-    __device__ __forceinline__ void load(const uint16_t *row, int lane, int /*L*/) {
-        v = __ldg(reinterpret_cast<const uint4 *>(row) + lane);
-    }
-    __device__ __forceinline__ uint32_t get(int j, int lane, int L) const {
-        const uint32_t w = (j < 2) ? v.x : (j < 4) ? v.y : (j < 6) ? v.z : v.w;
-        const uint32_t e = (j & 1) ? (w >> 16) : (w & 0xFFFFu);
-        if (FULLROW) return e;
-        return (lane * 8 + j < L) ? e : 0x10000u;       // padding entries never compare true
-    }
-};
-template <bool FULLROW>
-struct RowRegs<1, FULLROW> {
-    uint32_t v;
-    __device__ __forceinline__ void load(const uint16_t *row, int lane, int L) {
-        v = (FULLROW || lane < L) ? (uint32_t)__ldg(row + lane) : 0x10000u;
-    }
-    __device__ __forceinline__ uint32_t get(int, int, int) const { return v; }
 };
 
 // count of torchac.cpp:327 in the reference's modular 64-bit arithmetic (only needed when the code
@@ -225,62 +203,104 @@ struct CoderState {
     uint32_t low, high, value;
 };
 
-// one symbol: search the row, update [low, high], renormalise, shift code bits into `value`
-template <int EPL, bool FULLROW>
-__device__ __forceinline__ int decode_step(const RowRegs<EPL, FULLROW> &cur, CoderState &cs, BitSource &src,
-                                           int lane, int L, bool update) {
-    const uint32_t r = cs.high - cs.low;                        // span - 1
-    const uint32_t dv = cs.value - cs.low;
-    const uint64_t target = ((uint64_t)dv + 1ull) << 16;
+// CDF row held by a warp.  EPL = 8: lane l holds entries 8l..8l+7 (two per register) plus the first
+// entry of lane l+1; EPL = 1: lane l holds entry l.  Padding entries (index >= L) are stored as 0.
+template <int EPL>
+struct RowRegs;
+template <>
+struct RowRegs<8> {
+    uint4 v;
+    __device__ __forceinline__ void load(const uint16_t *row, int lane) {
+        v = __ldg(reinterpret_cast<const uint4 *>(row) + lane);
+    }
+};
+template <>
+struct RowRegs<1> {
+    uint32_t v;
+    __device__ __forceinline__ void load(const uint16_t *row, int lane) { v = (uint32_t)__ldg(row + lane); }
+};
+
+__device__ __forceinline__ bool below(uint32_t e, uint32_t r, uint64_t target) {   // e * (r+1) < target
+    return ((uint64_t)r * e + e) < target;
+}
+
+// Search the row for the symbol whose interval contains the code value.  Returns the symbol and
+// its bounds: c_lo = cdf[sym], c_hi = cdf[sym+1] (2^16 for the last symbol).
+//   reference: count = ((value-low+1)*2^16-1)/span; sym = largest m with cdf[m] <= count, floor 0
+//   here:      cdf[m] <= count  <=>  cdf[m]*span < (value-low+1)<<16      (no division)
+template <bool FULLROW>
+__device__ __forceinline__ int search_row(const RowRegs<8> &row, uint32_t r, uint64_t target, int lane, int L,
+                                          uint32_t &c_lo, uint32_t &c_hi) {
+    // every lane tests its 8 entries; rows are non-decreasing, so cdf[sym] is the largest "true" entry
+    // and cdf[sym+1] the smallest "false" one: two warp reductions (REDUX) + one for the index
+    const uint32_t w[4] = {row.v.x, row.v.y, row.v.z, row.v.w};
     uint32_t lane_lo = 0u, lane_hi = 0x10000u;
     int n_true = 0;
-    if (__builtin_expect(dv > r, 0)) {
-        // value outside [low, high]: reproduce the reference's arithmetic exactly
-        const uint32_t count16 = foreign_count16(cs.value, cs.low, r);
 #pragma unroll
-        for (int j = 0; j < EPL; ++j) {
-            const uint32_t e = cur.get(j, lane, L);
-            const bool f = (e <= count16) || (j == 0 && lane == 0);
-            lane_lo = f ? max(lane_lo, e) : lane_lo;
-            lane_hi = f ? lane_hi : min(lane_hi, e);
-            n_true += f ? 1 : 0;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < EPL; ++j) {
-            const uint32_t e = cur.get(j, lane, L);
-            const uint64_t prod = (uint64_t)r * e + e;          // e * span
-            const bool f = (prod < target) || (j == 0 && lane == 0);   // cdf[m] <= count; symbol 0 = floor
-            lane_lo = f ? max(lane_lo, e) : lane_lo;
-            lane_hi = f ? lane_hi : min(lane_hi, e);
-            n_true += f ? 1 : 0;
-        }
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t e = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xFFFFu);
+        const bool valid = FULLROW || (lane * 8 + j) < L;         // padding entries are never true
+        const bool f = ((lane | j) == 0) || (valid && below(e, r, target));
+        lane_lo = f ? max(lane_lo, e) : lane_lo;
+        lane_hi = (f || !valid) ? lane_hi : min(lane_hi, e);
+        n_true += f ? 1 : 0;
     }
-    const uint32_t c_lo = __reduce_max_sync(FULL, lane_lo);
-    const uint32_t c_hi = __reduce_min_sync(FULL, lane_hi);
-    const int sym = __reduce_add_sync(FULL, n_true) - 1;
+    c_lo = __reduce_max_sync(FULL, lane_lo);
+    c_hi = __reduce_min_sync(FULL, lane_hi);
+    return __reduce_add_sync(FULL, n_true) - 1;
+}
+
+template <bool FULLROW>
+__device__ __forceinline__ int search_row(const RowRegs<1> &row, uint32_t r, uint64_t target, int lane, int L,
+                                          uint32_t &c_lo, uint32_t &c_hi) {
+    const bool f = (lane == 0) || ((lane < L) && below(row.v, r, target));
+    const int n = __popc(__ballot_sync(FULL, f));
+    const int sym = n - 1;
+    c_lo = __shfl_sync(FULL, row.v, sym);
+    const uint32_t nxt = __shfl_sync(FULL, row.v, n & 31);
+    c_hi = (n >= L) ? 0x10000u : nxt;
+    return sym;
+}
+
+// one symbol: search, update [low, high], renormalise, shift code bits into `value`
+template <int EPL, bool FULLROW>
+__device__ __forceinline__ int decode_step(const RowRegs<EPL> &cur, CoderState &cs, BitSource &src, int lane, int L,
+                                           bool update) {
+    uint32_t r = cs.high - cs.low;                              // span - 1
+    const uint32_t dv = cs.value - cs.low;
+    uint64_t target = ((uint64_t)dv + 1ull) << 16;
+    uint32_t r_cmp = r;
+    if (__builtin_expect(dv > r, 0)) {
+        // value outside [low, high] (corrupt / foreign input): use the reference's truncated count;
+        // cdf[m] <= count  <=>  cdf[m] * 1 < count + 1
+        target = (uint64_t)foreign_count16(cs.value, cs.low, r) + 1ull;
+        r_cmp = 0u;
+    }
+    uint32_t c_lo, c_hi;
+    const int sym = search_row<FULLROW>(cur, r_cmp, target, lane, L, c_lo, c_hi);
     if (update) {
         const uint64_t p_hi = (uint64_t)r * c_hi + c_hi;
         const uint64_t p_lo = (uint64_t)r * c_lo + c_lo;
-        uint32_t high = cs.low - 1u + (uint32_t)(p_hi >> 16);
-        uint32_t low = cs.low + (uint32_t)(p_lo >> 16);
-        uint32_t value = cs.value;
-        const int k = __clz((int)(low ^ high));
-        if (k > 0) {
-            low <<= k;
-            high = (high << k) | ((1u << k) - 1u);
-            value = (value << k) | src.take(k);
+        const uint32_t high = cs.low - 1u + (uint32_t)(p_hi >> 16);
+        const uint32_t low = cs.low + (uint32_t)(p_lo >> 16);
+        // renormalisation: k "equal MSB" shifts, then u "underflow" shifts (see file header)
+        const uint32_t k = (uint32_t)__clz((int)(low ^ high));
+        const uint32_t y = low & ~high;
+        const uint32_t u = (uint32_t)__clz((int)~shl_c(shl_c(y, k), 1u));
+        const uint32_t s = k + u;
+        const uint32_t msb = u ? 0x80000000u : 0u;
+        if (__builtin_expect(s <= 32u, 1)) {
+            const uint32_t bits = src.take(s);
+            cs.low = shl_c(low, s) & ~msb;
+            cs.high = shl_c(high, s) | ~shl_c(0xFFFFFFFFu, s) | msb;
+            cs.value = (shl_c(cs.value, s) | bits) ^ msb;
+        } else {
+            const uint32_t bk = src.take(k);
+            const uint32_t bu = src.take(u);
+            cs.low = shl_c(shl_c(low, k), u) & ~msb;
+            cs.high = shl_c(shl_c(high, k) | ~shl_c(0xFFFFFFFFu, k), u) | ~shl_c(0xFFFFFFFFu, u) | msb;
+            cs.value = (shl_c(shl_c(cs.value, k) | bk, u) | bu) ^ msb;
         }
-        const uint32_t m = (low & ~high) << 1;
-        const int u = __clz((int)~m);
-        if (u > 0) {
-            low = (low << u) & 0x7FFFFFFFu;
-            high = (high << u) | 0x80000000u | ((1u << u) - 1u);
-            value = ((value << u) | src.take(u)) ^ 0x80000000u;
-        }
-        cs.low = low;
-        cs.high = high;
-        cs.value = value;
     }
     return sym;
 }
@@ -299,44 +319,52 @@ ac_decode_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, in
     const uint32_t last = (count > n - first) ? n : first + count;   // exclusive
 
     BitSource src;
-    src.open(st.in, st.in_len);
+    const uint32_t bit0 = src.open(st.in, st.in_len);
 
     CoderState cs;
     if (first == 0) {
         cs.low = 0u;
         cs.high = 0xFFFFFFFFu;
-        src.seek(0);
+        src.seek(bit0);
         cs.value = src.take(32);
     } else {
         cs.low = st.state[0];
         cs.high = st.state[1];
         cs.value = st.state[2];
-        src.seek(st.state[3]);
+        src.seek(st.state[3] + bit0);
     }
 
     const uint16_t *__restrict__ table = st.table;
     const int64_t pitch = st.row_pitch;
     uint8_t *__restrict__ sym_out = st.sym_out;
+    const bool vec_out = ((reinterpret_cast<uintptr_t>(sym_out) | first) & 3u) == 0u;
 
     // symbols handled by the unrolled main loop: whole groups of D, never the stream's final symbol
     const uint32_t upd_end = (last == n) ? n - 1 : last;          // symbols < upd_end update the state
     const uint32_t main_end = first + ((upd_end - first) / D) * D;
 
-    RowRegs<EPL, FULLROW> ring[D];
+    RowRegs<EPL> ring[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const uint32_t i = first + d;
-        if (i < last) ring[d].load(table + (int64_t)i * pitch, lane, L);
+        if (i < last) ring[d].load(table + (int64_t)i * pitch, lane);
     }
     uint32_t base = first;
     for (; base < main_end; base += D) {
+        uint32_t packed[D / 4];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             const uint32_t i = base + d;
-            const RowRegs<EPL, FULLROW> cur = ring[d];
-            if (i + D < last) ring[d].load(table + (int64_t)(i + D) * pitch, lane, L);
+            const RowRegs<EPL> cur = ring[d];
+            if (i + D < last) ring[d].load(table + (int64_t)(i + D) * pitch, lane);
             const int sym = decode_step<EPL, FULLROW>(cur, cs, src, lane, L, true);
-            if (lane == 0) sym_out[i] = (uint8_t)sym;
+            if ((d & 3) == 0) packed[d >> 2] = 0u;
+            packed[d >> 2] |= (uint32_t)sym << (8 * (d & 3));
+            if (!vec_out && lane == 0) sym_out[i] = (uint8_t)sym;
+        }
+        if (vec_out && lane == 0) {
+#pragma unroll
+            for (int q = 0; q < D / 4; ++q) *reinterpret_cast<uint32_t *>(sym_out + base + 4 * q) = packed[q];
         }
     }
     // tail (< D symbols, may contain the final symbol, which leaves the state untouched:
@@ -354,7 +382,7 @@ ac_decode_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, in
         st.state[0] = cs.low;
         st.state[1] = cs.high;
         st.state[2] = cs.value;
-        st.state[3] = src.consumed;
+        st.state[3] = src.pos - bit0;
     }
 }
 
@@ -409,9 +437,7 @@ extern "C" int l3c_ac_decode_streams(const l3c_dec_stream_t *streams_dev, int n_
     const int grid = ceil_div(n_streams, DEC_WARPS_PER_CTA);
     const dim3 blk(32 * DEC_WARPS_PER_CTA);
     cudaStream_t st = (cudaStream_t)stream;
-    if (L == 32) {
-        ac_decode_kernel<1, true><<<grid, blk, 0, st>>>(streams_dev, n_streams, L, first, count);
-    } else if (L < 32) {
+    if (L <= 32) {
         ac_decode_kernel<1, false><<<grid, blk, 0, st>>>(streams_dev, n_streams, L, first, count);
     } else if (L == 256) {
         ac_decode_kernel<8, true><<<grid, blk, 0, st>>>(streams_dev, n_streams, L, first, count);

@@ -66,15 +66,17 @@ class PackedConv(object):
         return self.w, self.b
 
     def get_tc(self):
-        """Tensor-core operand image of a 3x3 / 64-input-channel conv: [tap 9][K-half 2][Cout][32]
-        fp32, K-major rows of 128 B that TMA drops into 128B-swizzled shared memory."""
+        """Tensor-core operand image: [tap][K-half = Cin/32][Cout padded to 64][32] fp32, K-major rows
+        of 128 B that TMA drops into 128B-swizzled shared memory; values pre-rounded to TF32 (RN)."""
         _, b = self.get()
         if self.w_tc is None:
-            w = self.conv.weight.detach().float()
+            w = round_to_tf32(self.conv.weight.detach().float())
             cout, cin, kh, kw = w.shape
-            assert (cin, kh, kw) == (64, 3, 3)
-            w = round_to_tf32(w)
-            self.w_tc = w.permute(2, 3, 0, 1).reshape(9, cout, 2, 32).permute(0, 2, 1, 3).contiguous()
+            cout_pad = (cout + 63) // 64 * 64
+            assert cin % 64 == 0 and kh == kw and kh in (1, 3)
+            img = torch.zeros(kh * kw, cin // 32, cout_pad, 32, dtype=torch.float32, device=w.device)
+            img[:, :, :cout] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin // 32, 32).permute(0, 2, 1, 3)
+            self.w_tc = img.contiguous()
         return self.w_tc, b
 
 
@@ -110,11 +112,18 @@ def packed(conv):
     return _packed_obj(conv).get()
 
 
-def tc_eligible(conv, x_pitch, y_pitch, y_coff):
-    """Layers the tcgen05 kernel covers: 3x3 (any dilation), stride 1, 64 input channels in a
-    pitch-64 buffer, Cout a multiple of 64.  Everything else runs on the fp32 FFMA kernel."""
-    return (conv.kernel_size[0] == 3 and conv.stride[0] == 1 and conv.in_channels == 64 and x_pitch == 64 and
-            conv.out_channels % 64 == 0 and y_pitch % 4 == 0 and y_coff % 4 == 0)
+def tc_eligible(conv, x_pitch, y_pitch, y_coff, pixel_shuffle=False):
+    """Layers the tcgen05 kernel covers: 3x3 (any dilation) with 64 input channels and Cout % 64 == 0,
+    and 1x1 with Cin % 64 == 0 (any Cout); stride 1, dense input pitch.  Everything else (5x5/s2,
+    Cin = 3 or 5) runs on the fp32 FFMA kernel."""
+    k, cin, cout = conv.kernel_size[0], conv.in_channels, conv.out_channels
+    if conv.stride[0] != 1 or x_pitch != cin:
+        return False
+    if k == 3:
+        return cin == 64 and cout % 64 == 0 and y_pitch % 4 == 0 and y_coff % 4 == 0
+    if k == 1:
+        return cin % 64 == 0 and not pixel_shuffle
+    return False
 
 
 # ----------------------------------------------------------------------------------------------
@@ -150,7 +159,7 @@ def conv2d(conv, x, cin=None, relu=False, residual=None, pixel_shuffle=False, ou
     mode = _PRECISION['mode'] if precision is None else precision
     prec = mode
     x_in = x
-    if mode != _lib.PREC_FP32 and tc_eligible(conv, xp, out.shape[-1], out_coff) and cin == 64:
+    if mode != _lib.PREC_FP32 and tc_eligible(conv, xp, out.shape[-1], out_coff, pixel_shuffle) and cin == conv.in_channels:
         w, b = _packed_obj(conv).get_tc()
         if xa.r is not None:
             x_in = xa.r                       # TF32-rounded operand image

@@ -234,7 +234,9 @@ class StackedAtrousConvs(nn.Module):
         N, H, W, Cin = x.f.shape
         cat = torch.empty(N, H, W, Cin * len(self.atrous), dtype=torch.float32, device=x.f.device)
         for i, a in enumerate(self.atrous):
-            E.conv2d(a, x, out=cat, out_coff=i * Cin)                 # concat by channel slice
+            # concat by channel slice; `cat` only feeds the 1x1 conv -> TF32-rounded in place when the
+            # tensor cores are on
+            E.conv2d(a, x, out=cat, out_coff=i * Cin, want='round')
         return E.conv2d(self.lin, cat)
 
 

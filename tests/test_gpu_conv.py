@@ -163,3 +163,16 @@ def test_tcgen05_conv_vs_torch_on_tf32_operands(cout, rate, H, W, kw):
     assert torch.equal(got.r.cpu(), E.round_to_tf32(got.f.cpu()))
     r_only = E.conv2d(conv.cuda(), xa, precision=_lib.PREC_TF32, want='round', **kw)
     assert torch.equal(r_only.f.cpu(), got.r.cpu())
+
+
+@pytest.mark.parametrize('cin,cout,H,W', [(192, 120, 9, 31), (192, 150, 16, 16), (64, 64, 8, 16)])
+def test_tcgen05_1x1_conv(cin, cout, H, W):
+    """1x1 convs with Cin % 64 == 0 (the 192 -> Kp head of the probability classifier) also run on the
+    tensor cores; Cout need not be a multiple of 64 (weight image is zero padded, stores are guarded)."""
+    from l3c_pytorch_b200 import engine as E, _lib
+    conv = _conv_module(cin, cout, 1)
+    x = E.round_to_tf32(torch.randn(2, cin, H, W))
+    want = F.conv2d(x, E.round_to_tf32(conv.weight.detach()), conv.bias.detach())
+    got = E.conv2d(conv.cuda(), _nhwc(x), precision=_lib.PREC_TF32)
+    assert got.shape == (2, H, W, cout)
+    np.testing.assert_allclose(got.cpu().permute(0, 3, 1, 2).numpy(), want.numpy(), rtol=1e-4, atol=1e-4)
