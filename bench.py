@@ -101,6 +101,10 @@ def cpu_roundtrip_mpx_s(n_images, hw, first_image=0):
     from l3c_pytorch_b200 import config
     from l3c_pytorch_b200.blueprint import MultiscaleBlueprint
     from oracle import model as om
+    try:        # torchrun pins OMP_NUM_THREADS=1; the CPU reference gets all host cores it may use
+        torch.set_num_threads(max(torch.get_num_threads(), len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     torch.manual_seed(0)
     bp = MultiscaleBlueprint(config.ms_config('cr'), device='cpu')
     sd = {k: v.detach().cpu() for k, v in bp.net.state_dict().items()}
@@ -224,8 +228,10 @@ def run_ours(args):
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    launches0 = E.LAUNCHES['n']
     for s in range(args.steps):
         S, info = step_resident(dev_sets[s % n_sets])
+    launches_timed = E.LAUNCHES['n'] - launches0
     e1.record()
     barrier()
     t_wall1 = time.time()
@@ -316,26 +322,13 @@ def run_ours(args):
             'roofline': roofline,
             'cpu_baseline': cpu,
         }
-        # launches: count them from the structure of one step (all are kernels of libl3c_b200.so)
-        line['gpu_launches'] = count_launches(bp) * args.steps
+        # kernels of libl3c_b200.so launched inside the timed (device-resident) region, counted at the
+        # C-ABI call sites (engine.LAUNCHES)
+        line['gpu_launches'] = launches_timed
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
-
-
-def count_launches(bp):
-    """Kernels of libl3c_b200.so launched by one encode+decode round trip of one batch."""
-    net = bp.net
-    S = net.scales
-    convs_enc = 0 if net._rgb else S * (1 + 1 + 17)               # head, down, 8 ResBlocks*2 + 1
-    convs_dec = S * (1 + 17 + 1)                                    # head, body, tail
-    convs_prob = S * 4
-    fwd = (0 if net._rgb else 1) + convs_enc + S + convs_dec + convs_prob   # rgb_prep, quantize heads
-    enc_entropy = (S + 1) + 1 + 1                                   # intervals per scale, coder, gather
-    dec_net = convs_dec + convs_prob + S                            # + symbols_to_values
-    dec_entropy = 1 + (S - 1) * 2 + 3 * 2                           # uniform; z scales; RGB per channel
-    return fwd + enc_entropy + dec_net + dec_entropy
 
 
 def main():

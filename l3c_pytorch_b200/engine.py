@@ -13,6 +13,7 @@ from . import _lib
 from ._lib import lib, check, ConvDesc
 
 # default conv precision: env L3C_CONV_PRECISION (fp32 | tf32); see set_conv_precision
+LAUNCHES = {'n': 0}        # kernels of libl3c_b200.so launched through this module (bench.py reports it)
 _PRECISION = {'mode': _lib.PRECISIONS[os.environ.get('L3C_CONV_PRECISION', 'fp32')]}
 
 
@@ -181,6 +182,7 @@ def conv2d(conv, x, cin=None, relu=False, residual=None, pixel_shuffle=False, ou
     if residual is not None:
         assert residual.shape == out.shape and residual.is_contiguous()
     check(lib.l3c_conv2d(ctypes.byref(d), _stream_ptr()))
+    LAUNCHES['n'] += 1
     if want == 'plain':
         return out
     if want == 'round':
@@ -207,6 +209,7 @@ def rgb_prep(img_u8, conv1, conv2):
         xsub = torch.empty(N, H, W, 3, dtype=torch.float32, device=img_u8.device)
     check(lib.l3c_rgb_prep(_ptr(img_u8), _ptr(A1), _ptr(b1), _ptr(A2), _ptr(b2), N, H * W,
                            _ptr(xsub), _ptr(t), _stream_ptr()))
+    LAUNCHES['n'] += 1
     return xsub, t
 
 
@@ -221,6 +224,7 @@ def quantize_head(f, to_q_conv, levels):
     bnq = torch.empty(N, H, W, 8, dtype=torch.float32, device=f.device)
     check(lib.l3c_quantize_head(_ptr(f), _ptr(w), _ptr(b), _ptr(lev), N, H * W, Cf, C, lev.numel(),
                                 _ptr(sym), _ptr(bnq), _stream_ptr()))
+    LAUNCHES['n'] += 1
     return sym, bnq
 
 
@@ -230,6 +234,7 @@ def symbols_to_values(sym, values, shift=None):
     out = torch.empty(N, H, W, 8, dtype=torch.float32, device=sym.device)
     check(lib.l3c_symbols_to_values(_ptr(sym), _ptr(values), _ptr(shift), N, H * W, C, values.numel(),
                                     _ptr(out), _stream_ptr()))
+    LAUNCHES['n'] += 1
     return out
 
 
@@ -238,6 +243,7 @@ def bicubic_half(img_u8):
     assert C == 3 and img_u8.dtype == torch.uint8 and img_u8.is_contiguous()
     out = torch.empty(N, 3, int(H * 0.5), int(W * 0.5), dtype=torch.uint8, device=img_u8.device)
     check(lib.l3c_bicubic_half_u8(_ptr(img_u8), N, H, W, _ptr(out), _stream_ptr()))
+    LAUNCHES['n'] += 2
     return out
 
 
@@ -256,6 +262,7 @@ def dmll_intervals(l, sym, targets, C, K, L, rgb):
     iv = torch.empty(N, C, H * W, dtype=torch.int32, device=l.device)
     check(lib.l3c_dmll_intervals(_ptr(l), _ptr(sym), _ptr(targets), N, H * W, C, K, L, int(rgb),
                                  _ptr(iv), _stream_ptr()))
+    LAUNCHES['n'] += 1
     return iv
 
 
@@ -263,6 +270,7 @@ def lut_intervals(sym, lut):
     iv = torch.empty(sym.shape[0], sym.shape[1], sym.shape[2] * sym.shape[3], dtype=torch.int32,
                      device=sym.device)
     check(lib.l3c_lut_intervals(_ptr(sym), _ptr(lut), sym.numel(), _ptr(iv), _stream_ptr()))
+    LAUNCHES['n'] += 1
     return iv
 
 
@@ -275,6 +283,7 @@ def dmll_build_table(l, sym, targets, C, K, L, rgb, c, table, pix0=0, npix=None)
     npix = H * W - pix0 if npix is None else npix
     check(lib.l3c_dmll_build_table(_ptr(l), _ptr(sym), _ptr(targets), N, H * W, C, K, L, int(rgb), c,
                                    pix0, npix, _ptr(table), table_pitch(L), _stream_ptr()))
+    LAUNCHES['n'] += 1
 
 
 def dmll_nll(l, sym, values, C, K, L, rgb, x_min, x_max, want_map=False):
@@ -284,6 +293,7 @@ def dmll_nll(l, sym, values, C, K, L, rgb, x_min, x_max, want_map=False):
     nmap = torch.empty(N, C, H, W, dtype=torch.float32, device=l.device) if want_map else None
     check(lib.l3c_dmll_nll(_ptr(l), _ptr(sym), _ptr(values), N, H * W, C, K, L, int(rgb),
                            float(x_min), float(x_max), _ptr(out), _ptr(nmap), _stream_ptr()))
+    LAUNCHES['n'] += 2
     return out, nmap
 
 
@@ -294,6 +304,7 @@ def dmll_channel_params(l, x_dec, C, K, rgb, c):
     outs = [torch.empty(N, K, H, W, dtype=torch.float32, device=l.device) for _ in range(3)]
     check(lib.l3c_dmll_channel_params(_ptr(l), _ptr(x_dec), N, H * W, C, K, int(rgb), c,
                                       _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _stream_ptr()))
+    LAUNCHES['n'] += 1
     return outs
 
 
@@ -311,12 +322,14 @@ def ac_encode_streams(desc_np, device):
     desc = _desc_to_device(desc_np, device)
     lens = torch.empty(n, dtype=torch.int32, device=device)
     check(lib.l3c_ac_encode_streams(_ptr(desc), n, _ptr(lens), _stream_ptr()))
+    LAUNCHES['n'] += 1
     return desc, lens
 
 
 def pack_streams(desc_dev, lens_dev, dst_off_np, n, blob):
     off = torch.from_numpy(dst_off_np.astype(np.int64)).to(blob.device)
     check(lib.l3c_pack_streams(_ptr(desc_dev), _ptr(lens_dev), _ptr(off), n, _ptr(blob), _stream_ptr()))
+    LAUNCHES['n'] += 1
 
 
 def ac_decode_streams(desc_np, device, L, first=0, count=None, desc_dev=None, n=None):
@@ -329,4 +342,5 @@ def ac_decode_streams(desc_np, device, L, first=0, count=None, desc_dev=None, n=
     if count is None:
         count = int(desc_np['n_sym'].max()) if n else 0
     check(lib.l3c_ac_decode_streams(_ptr(desc_dev), n, L, first, count, _stream_ptr()))
+    LAUNCHES['n'] += 1
     return desc_dev
