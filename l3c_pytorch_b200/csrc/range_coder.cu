@@ -26,6 +26,16 @@ constexpr int DEC_WARPS_PER_CTA = 1;
 // ---------------------------------------------------------------------------------------------
 // encoder
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t shl_c(uint32_t x, uint32_t n) {   // x << n, 0 for n >= 32 (PTX clamps)
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+    return r;
+}
+__device__ __forceinline__ uint32_t shr_c(uint32_t x, uint32_t n) {   // x >> n, 0 for n >= 32
+    uint32_t r;
+    asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+    return r;
+}
 struct BitSink {
     uint32_t *out;       // word pointer (big-endian words)
     uint32_t cap_words;
@@ -92,28 +102,24 @@ ac_encode_kernel(const l3c_enc_stream_t *__restrict__ streams, int n_streams,
             high = low - 1u + (uint32_t)(p_hi >> 16);
             low = low + (uint32_t)(p_lo >> 16);
 
-            const int k = __clz((int)(low ^ high));          // leading bits already decided
-            if (k > 0) {
-                if (pending == 0u) {
-                    sink.put(low >> (32 - k), k);
-                } else {
-                    const uint32_t b0 = low >> 31;
-                    sink.put(b0, 1);
-                    sink.put_run(b0 ^ 1u, pending);
-                    pending = 0u;
-                    if (k > 1) sink.put((low << 1) >> (33 - k), k - 1);
-                }
-                low <<= k;
-                high = (high << k) | ((1u << k) - 1u);
+            // renormalisation: k "equal MSB" shifts, then u "underflow" shifts, done as one shift by s
+            const uint32_t k = (uint32_t)__clz((int)(low ^ high));
+            const uint32_t u = (uint32_t)__clz((int)~shl_c(shl_c(low & ~high, k), 1u));
+            const uint32_t s = k + u;
+            const uint32_t msb = u ? 0x80000000u : 0u;
+            const uint32_t top_bits = shr_c(low, 32u - k);               // the k decided bits (k = 0 -> 0)
+            if (__builtin_expect(pending == 0u || k == 0u, 1)) {
+                sink.put(top_bits, (int)k);                              // put(x, 0) is a no-op
+            } else {
+                const uint32_t b0 = top_bits >> (k - 1u);
+                sink.put(b0, 1);
+                sink.put_run(b0 ^ 1u, pending);
+                pending = 0u;
+                sink.put(top_bits & ~(1u << (k - 1u)), (int)k - 1);
             }
-            // underflow: low = 01..., high = 10...: drop the second MSB as often as that holds
-            const uint32_t m = (low & ~high) << 1;
-            const int u = __clz((int)~m);
-            if (u > 0) {
-                pending += (uint32_t)u;
-                low = (low << u) & 0x7FFFFFFFu;
-                high = (high << u) | 0x80000000u | ((1u << u) - 1u);
-            }
+            pending += u;
+            low = shl_c(low, s) & ~msb;
+            high = shl_c(high, s) | ~shl_c(0xFFFFFFFFu, s) | msb;
         }
     }
 
@@ -133,16 +139,6 @@ ac_encode_kernel(const l3c_enc_stream_t *__restrict__ streams, int n_streams,
 // ---------------------------------------------------------------------------------------------
 // decoder
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t shl_c(uint32_t x, uint32_t n) {   // x << n, 0 for n >= 32 (PTX clamps)
-    uint32_t r;
-    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
-    return r;
-}
-__device__ __forceinline__ uint32_t shr_c(uint32_t x, uint32_t n) {   // x >> n, 0 for n >= 32
-    uint32_t r;
-    asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
-    return r;
-}
 
 // MSB-first bit reader over a byte stream that may start at ANY address (streams are decoded in
 // place from the container): words are fetched from the 4-byte aligned address below the stream and
@@ -387,6 +383,272 @@ ac_decode_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// decoder, 256-symbol alphabets (the RGB streams): CTA = decoder warp + helper warp per stream
+//
+// A single warp issues one dependent instruction every ~4-5 cycles, so the serial rate of the coder
+// is set by the number of instructions the decoding warp executes per symbol.  Everything that does
+// not depend on the coder state is therefore moved to a second warp (another scheduler of the SM):
+//   helper warp : prefetches CDF rows from HBM one group (8 symbols) ahead, turns every entry m into
+//                 the packed proposal (cdf[m] << 16) | (cdf[m+1] - 1) and stores the row in a shared
+//                 memory ring; later turns the decoder's winning proposals into symbol indices
+//                 (number of proposals <= winner, minus 1) and writes them out.
+//   decoder warp: computes the reference's `count` exactly (float estimate + 64-bit integer
+//                 correction, no division), compares its 8 proposals against (count << 16 | 0xFFFF)
+//                 with ONE integer compare each, takes ONE warp max-reduction (rows are sorted, so
+//                 the last proposal whose cdf[m] <= count is the largest) and gets both interval
+//                 bounds from it; then the usual update / clz renormalisation / bit refill.
+// Hand-over by two mbarrier pairs (full/empty per group of 8 ring slots).
+// ---------------------------------------------------------------------------------------------
+namespace v3 {
+
+constexpr int G = 8;            // symbols per group
+constexpr int R = 2 * G;        // ring slots
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// Estimate of count = ((value - low + 1) * 2^16 - 1) / span (torchac.cpp:327), accurate to +-1.
+// The decoder does not correct it up front: it searches with the estimate and then VERIFIES the
+// interval it found against the exact integer condition  c_lo*span <= num < c_hi*span  (both products
+// are needed for the state update anyway); a miss (estimate off by one AND a CDF entry exactly at the
+// boundary) re-runs the search with the neighbouring count.
+__device__ __forceinline__ uint32_t estimate_count(uint32_t dv, uint32_t r) {
+    const float x = __uint2float_rn(dv) + 1.0f;
+    const float y = __uint2float_rn(r) + 1.0f;
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(y));
+    return __float2uint_rz(x * inv * 65536.0f);                      // may be 65536 when dv == r
+}
+
+__global__ void __launch_bounds__(64)
+ac_decode256_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, uint32_t first, uint32_t count) {
+    __shared__ __align__(16) uint4 ring[R][2][32];      // proposals: [slot][half][lane]
+    __shared__ uint32_t tops[R];                        // winning proposal per slot (decoder -> helper)
+    __shared__ __align__(8) uint64_t bars[4];           // full[0..1], empty[0..1]
+
+    const int sid = blockIdx.x;
+    if (sid >= n_streams) return;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const l3c_dec_stream_t st = streams[sid];
+    const uint32_t n = st.n_sym;
+    if (first >= n) return;
+    const uint32_t last = (count > n - first) ? n : first + count;   // exclusive
+    const uint32_t n_groups = (last - first + G - 1) / G;
+
+    const uint32_t bar0 = smem_u32(bars);
+    if (threadIdx.x == 0) {
+        mbar_init(bar0 + 0, 32);
+        mbar_init(bar0 + 8, 32);
+        mbar_init(bar0 + 16, 32);
+        mbar_init(bar0 + 24, 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 1) {
+        // ============================ helper warp ============================
+        const uint16_t *__restrict__ table = st.table;
+        const int64_t pitch = st.row_pitch;
+        uint8_t *__restrict__ sym_out = st.sym_out;
+        uint4 nxt[G];
+#pragma unroll
+        for (int d = 0; d < G; ++d) {
+            const uint32_t i = first + d;
+            if (i < last) nxt[d] = __ldg(reinterpret_cast<const uint4 *>(table + (int64_t)i * pitch) + lane);
+        }
+        for (uint32_t gi = 0; gi < n_groups + 2; ++gi) {
+            const uint32_t g = gi & 1u;
+            uint4 cur[G];
+#pragma unroll
+            for (int d = 0; d < G; ++d) cur[d] = nxt[d];
+            if (gi + 1 < n_groups) {
+#pragma unroll
+                for (int d = 0; d < G; ++d) {
+                    const uint32_t i = first + (gi + 1) * G + d;
+                    if (i < last) nxt[d] = __ldg(reinterpret_cast<const uint4 *>(table + (int64_t)i * pitch) + lane);
+                }
+            }
+            if (gi >= 2) {
+                // the decoder is done with the rows that live in this half of the ring: turn its
+                // winning proposals into symbols, then the slots may be overwritten
+                mbar_wait(bar0 + 16 + 8 * g, ((gi >> 1) - 1) & 1u);
+                const uint32_t ibase = first + (gi - 2) * G;
+                uint32_t pack0 = 0u, pack1 = 0u;
+#pragma unroll
+                for (int d = 0; d < G; ++d) {
+                    if (ibase + d < last) {
+                        const uint32_t top = tops[g * G + d];
+                        const uint4 a = ring[g * G + d][0][lane];
+                        const uint4 b = ring[g * G + d][1][lane];
+                        int c = (a.x <= top) + (a.y <= top) + (a.z <= top) + (a.w <= top) + (b.x <= top) + (b.y <= top) +
+                                (b.z <= top) + (b.w <= top);
+                        int tot = __reduce_add_sync(FULL, c);
+                        tot = tot > 0 ? tot - 1 : 0;
+                        if (d < 4) pack0 |= (uint32_t)tot << (8 * d);
+                        else pack1 |= (uint32_t)tot << (8 * (d - 4));
+                    }
+                }
+                if (lane == 0) {
+                    const bool vec = ((reinterpret_cast<uintptr_t>(sym_out) | ibase) & 3u) == 0u && ibase + G <= last;
+                    if (vec) {
+                        *reinterpret_cast<uint32_t *>(sym_out + ibase) = pack0;
+                        *reinterpret_cast<uint32_t *>(sym_out + ibase + 4) = pack1;
+                    } else {
+                        for (int d = 0; d < G; ++d)
+                            if (ibase + d < last)
+                                sym_out[ibase + d] = (uint8_t)(((d < 4 ? pack0 : pack1) >> (8 * (d & 3))) & 0xFFu);
+                    }
+                }
+                __syncwarp();
+            }
+            if (gi < n_groups) {
+#pragma unroll
+                for (int d = 0; d < G; ++d) {
+                    const uint4 v = cur[d];
+                    uint32_t nx = __shfl_down_sync(FULL, v.x, 1);
+                    if (lane == 31) nx = 0u;                                  // row end -> upper bound 2^16
+                    uint4 lo, hi;
+                    // proposal of entry m: (cdf[m] << 16) | ((cdf[m+1] - 1) & 0xFFFF)
+                    lo.x = (v.x << 16) | (((v.x >> 16) - 1u) & 0xFFFFu);
+                    lo.y = (v.x & 0xFFFF0000u) | (((v.y & 0xFFFFu) - 1u) & 0xFFFFu);
+                    lo.z = (v.y << 16) | (((v.y >> 16) - 1u) & 0xFFFFu);
+                    lo.w = (v.y & 0xFFFF0000u) | (((v.z & 0xFFFFu) - 1u) & 0xFFFFu);
+                    hi.x = (v.z << 16) | (((v.z >> 16) - 1u) & 0xFFFFu);
+                    hi.y = (v.z & 0xFFFF0000u) | (((v.w & 0xFFFFu) - 1u) & 0xFFFFu);
+                    hi.z = (v.w << 16) | (((v.w >> 16) - 1u) & 0xFFFFu);
+                    hi.w = (v.w & 0xFFFF0000u) | (((nx & 0xFFFFu) - 1u) & 0xFFFFu);
+                    ring[g * G + d][0][lane] = lo;
+                    ring[g * G + d][1][lane] = hi;
+                }
+                mbar_arrive(bar0 + 8 * g);                                    // full[g]
+            }
+        }
+        return;
+    }
+
+    // ============================ decoder warp ============================
+    BitSource src;
+    const uint32_t bit0 = src.open(st.in, st.in_len);
+    CoderState cs;
+    if (first == 0) {
+        cs.low = 0u;
+        cs.high = 0xFFFFFFFFu;
+        src.seek(bit0);
+        cs.value = src.take(32);
+    } else {
+        cs.low = st.state[0];
+        cs.high = st.state[1];
+        cs.value = st.state[2];
+        src.seek(st.state[3] + bit0);
+    }
+    for (uint32_t gi = 0; gi < n_groups; ++gi) {
+        const uint32_t g = gi & 1u;
+        mbar_wait(bar0 + 8 * g, (gi >> 1) & 1u);                              // full[g]
+        const uint32_t ibase = first + gi * G;
+#pragma unroll
+        for (int d = 0; d < G; ++d) {
+            const uint32_t i = ibase + d;
+            if (i < last) {
+                const uint4 a = ring[g * G + d][0][lane];
+                const uint4 b = ring[g * G + d][1][lane];
+                const uint32_t r = cs.high - cs.low;
+                const uint32_t dv = cs.value - cs.low;
+                const bool foreign = dv > r;                                  // corrupt / foreign input only
+                uint32_t q = foreign ? foreign_count16(cs.value, cs.low, r) : min(estimate_count(dv, r), 65535u);
+                const uint64_t num = ((uint64_t)dv << 16) | 0xFFFFull;        // (dv+1)*2^16 - 1
+                uint32_t top;
+                uint64_t p_hi, p_lo;
+                for (;;) {
+                    const uint32_t thr = (q << 16) | 0xFFFFu;
+                    // rows are sorted: the last proposal with cdf[m] <= count is the numerically largest
+                    uint32_t best = (lane == 0) ? a.x : 0u;                   // symbol 0 is the floor
+                    best = (a.x <= thr) ? a.x : best;
+                    best = (a.y <= thr) ? a.y : best;
+                    best = (a.z <= thr) ? a.z : best;
+                    best = (a.w <= thr) ? a.w : best;
+                    best = (b.x <= thr) ? b.x : best;
+                    best = (b.y <= thr) ? b.y : best;
+                    best = (b.z <= thr) ? b.z : best;
+                    best = (b.w <= thr) ? b.w : best;
+                    top = __reduce_max_sync(FULL, best);
+                    const uint32_t c_lo = top >> 16;
+                    const uint32_t c_hi = (top & 0xFFFFu) + 1u;
+                    p_hi = (uint64_t)r * c_hi + c_hi;                         // c_hi * span
+                    p_lo = (uint64_t)r * c_lo + c_lo;                         // c_lo * span
+                    if (foreign) break;
+                    // exact check of  c_lo <= count < c_hi  (c_lo > count can also mean "below the floor
+                    // of the row": then symbol 0 is right and lowering q cannot change the answer)
+                    if (__builtin_expect(p_hi <= num, 0)) { q += 1u; continue; }
+                    if (__builtin_expect(p_lo > num && q > 0u, 0)) {
+                        // either the estimate is one too high with an entry exactly on the boundary, or
+                        // the value is below the first entry (then q-1 finds the same floor symbol)
+                        const uint32_t thr2 = ((q - 1u) << 16) | 0xFFFFu;
+                        uint32_t b2 = (lane == 0) ? a.x : 0u;
+                        b2 = (a.x <= thr2) ? a.x : b2; b2 = (a.y <= thr2) ? a.y : b2;
+                        b2 = (a.z <= thr2) ? a.z : b2; b2 = (a.w <= thr2) ? a.w : b2;
+                        b2 = (b.x <= thr2) ? b.x : b2; b2 = (b.y <= thr2) ? b.y : b2;
+                        b2 = (b.z <= thr2) ? b.z : b2; b2 = (b.w <= thr2) ? b.w : b2;
+                        const uint32_t top2 = __reduce_max_sync(FULL, b2);
+                        if (top2 != top) { q -= 1u; continue; }
+                    }
+                    break;
+                }
+                if (lane == 0) tops[g * G + d] = top;
+                if (i != n - 1) {                                             // torchac.cpp:335-337
+                    const uint32_t high = cs.low - 1u + (uint32_t)(p_hi >> 16);
+                    const uint32_t low = cs.low + (uint32_t)(p_lo >> 16);
+                    const uint32_t k = (uint32_t)__clz((int)(low ^ high));
+                    const uint32_t y = low & ~high;
+                    const uint32_t u = (uint32_t)__clz((int)~shl_c(shl_c(y, k), 1u));
+                    const uint32_t s = k + u;
+                    const uint32_t msb = u ? 0x80000000u : 0u;
+                    if (__builtin_expect(s <= 32u, 1)) {
+                        const uint32_t bits = src.take(s);
+                        cs.low = shl_c(low, s) & ~msb;
+                        cs.high = shl_c(high, s) | ~shl_c(0xFFFFFFFFu, s) | msb;
+                        cs.value = (shl_c(cs.value, s) | bits) ^ msb;
+                    } else {
+                        const uint32_t bk = src.take(k);
+                        const uint32_t bu = src.take(u);
+                        cs.low = shl_c(shl_c(low, k), u) & ~msb;
+                        cs.high = shl_c(shl_c(high, k) | ~shl_c(0xFFFFFFFFu, k), u) | ~shl_c(0xFFFFFFFFu, u) | msb;
+                        cs.value = (shl_c(shl_c(cs.value, k) | bk, u) | bu) ^ msb;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        mbar_arrive(bar0 + 16 + 8 * g);                                       // empty[g]
+    }
+    if (lane == 0 && st.state != nullptr) {
+        st.state[0] = cs.low;
+        st.state[1] = cs.high;
+        st.state[2] = cs.value;
+        st.state[3] = src.pos - bit0;
+    }
+}
+
+}  // namespace v3
+
+// ---------------------------------------------------------------------------------------------
 // gather the variable-length code streams into one contiguous blob (container layout, byte offsets)
 // ---------------------------------------------------------------------------------------------
 constexpr int PACK_CHUNK = 16384;
@@ -440,7 +702,7 @@ extern "C" int l3c_ac_decode_streams(const l3c_dec_stream_t *streams_dev, int n_
     if (L <= 32) {
         ac_decode_kernel<1, false><<<grid, blk, 0, st>>>(streams_dev, n_streams, L, first, count);
     } else if (L == 256) {
-        ac_decode_kernel<8, true><<<grid, blk, 0, st>>>(streams_dev, n_streams, L, first, count);
+        v3::ac_decode256_kernel<<<n_streams, 64, 0, st>>>(streams_dev, n_streams, first, count);
     } else {
         ac_decode_kernel<8, false><<<grid, blk, 0, st>>>(streams_dev, n_streams, L, first, count);
     }
