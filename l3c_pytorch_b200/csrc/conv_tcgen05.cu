@@ -151,6 +151,99 @@ struct Params {
     int cout_rows;   // rows per (tap, K-half) slab of the weight image = cout_tiles * 64
 };
 
+// 4-warp epilogue shared by both kernels: TMEM -> registers -> bias / ReLU / residual / TF32 twin ->
+// global (NHWC, channel slice, or PixelShuffle(2) addressing).  Tile t of this CTA's sequence
+// t0, t0+tstride, ... ; `ct_fixed` >= 0 pins the Cout tile (kernel v2), else it is decoded from t.
+__device__ __forceinline__ void epilogue_loop(const Params &p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                              int warp, int lane, int t0, int tstride, int t_end, int ct_fixed) {
+    const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 are this warp's
+    const int m = quarter * 32 + lane;            // pixel row of the tile
+    uint32_t acc = 0, acc_phase = 0;
+    const bool relu = (p.flags & L3C_CONV_RELU) != 0;
+    const bool shuffle = (p.flags & L3C_CONV_PIXEL_SHUFFLE2) != 0;
+    const bool round_y = (p.flags & L3C_CONV_ROUND_TF32) != 0;
+    for (int t = t0; t < t_end; t += tstride) {
+        int q = t;
+        int ct = ct_fixed;
+        if (ct_fixed < 0) { ct = q % p.cout_tiles; q /= p.cout_tiles; }
+        const int tx = q % p.tiles_x; q /= p.tiles_x;
+        const int ty = q % p.tiles_y; q /= p.tiles_y;
+        const int n = q;
+        const int oy = ty * TH + (m >> 4);
+        const int ox = tx * TW + (m & 15);
+        const bool inside = (oy < p.H) && (ox < p.W);
+        mbar_wait(tfull0 + 8u * acc, acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            float v[16];
+            tmem_ld16(taddr + c0, v);
+            const int co0 = ct * 64 + c0;
+            if (inside && co0 < p.Cout) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] += __ldg(p.bias + co0 + i);          // bias is padded to cout_rows
+                    if (relu) v[i] = fmaxf(v[i], 0.f);
+                }
+                if (!shuffle) {
+                    const size_t off = (((size_t)n * p.H + oy) * p.W + ox) * p.y_pitch + p.y_coff + co0;
+                    const bool vec = (((p.y_pitch | p.y_coff) & 3) == 0) && (co0 + 16 <= p.Cout);
+                    if (vec) {
+                        if (p.residual) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 r = __ldg(reinterpret_cast<const float4 *>(p.residual + off + i));
+                                v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
+                            }
+                        }
+                        if (p.y_tf32) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4)
+                                *reinterpret_cast<float4 *>(p.y_tf32 + off + i) =
+                                    make_float4(round_tf32(v[i]), round_tf32(v[i + 1]), round_tf32(v[i + 2]),
+                                                round_tf32(v[i + 3]));
+                        }
+                        if (round_y) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = round_tf32(v[i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4 *>(p.y + off + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if (co0 + i < p.Cout) {
+                                float o = v[i];
+                                if (p.residual) o += __ldg(p.residual + off + i);
+                                if (p.y_tf32) p.y_tf32[off + i] = round_tf32(o);
+                                p.y[off + i] = round_y ? round_tf32(o) : o;
+                            }
+                        }
+                    }
+                } else {
+                    // out[n, 2*oy+i, 2*ox+j, cq] = conv[n, oy, ox, 4*cq + 2*i + j]
+                    const int H2 = p.H * 2, W2 = p.W * 2;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int co = co0 + i;
+                        const int cq = co >> 2, si = (co >> 1) & 1, sj = co & 1;
+                        const size_t o2 = (((size_t)n * H2 + 2 * oy + si) * W2 + 2 * ox + sj) * p.y_pitch + p.y_coff + cq;
+                        if (p.y_tf32) p.y_tf32[o2] = round_tf32(v[i]);
+                        p.y[o2] = round_y ? round_tf32(v[i]) : v[i];
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                        const Params p) {
@@ -259,91 +352,7 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
-        const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 are this warp's
-        const int m = quarter * 32 + lane;            // pixel row of the tile
-        uint32_t acc = 0, acc_phase = 0;
-        const bool relu = (p.flags & L3C_CONV_RELU) != 0;
-        const bool shuffle = (p.flags & L3C_CONV_PIXEL_SHUFFLE2) != 0;
-        const bool round_y = (p.flags & L3C_CONV_ROUND_TF32) != 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            int q = t;
-            const int ct = q % p.cout_tiles; q /= p.cout_tiles;
-            const int tx = q % p.tiles_x; q /= p.tiles_x;
-            const int ty = q % p.tiles_y; q /= p.tiles_y;
-            const int n = q;
-            const int oy = ty * TH + (m >> 4);
-            const int ox = tx * TW + (m & 15);
-            const bool inside = (oy < p.H) && (ox < p.W);
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-            for (int c0 = 0; c0 < 64; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + c0, v);
-                const int co0 = ct * 64 + c0;
-                if (inside && co0 < p.Cout) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        v[i] += __ldg(p.bias + co0 + i);          // bias is padded to cout_rows
-                        if (relu) v[i] = fmaxf(v[i], 0.f);
-                    }
-                    if (!shuffle) {
-                        const size_t off = (((size_t)n * p.H + oy) * p.W + ox) * p.y_pitch + p.y_coff + co0;
-                        const bool vec = (((p.y_pitch | p.y_coff) & 3) == 0) && (co0 + 16 <= p.Cout);
-                        if (vec) {
-                            if (p.residual) {
-#pragma unroll
-                                for (int i = 0; i < 16; i += 4) {
-                                    const float4 r = __ldg(reinterpret_cast<const float4 *>(p.residual + off + i));
-                                    v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
-                                }
-                            }
-                            if (p.y_tf32) {
-#pragma unroll
-                                for (int i = 0; i < 16; i += 4)
-                                    *reinterpret_cast<float4 *>(p.y_tf32 + off + i) =
-                                        make_float4(round_tf32(v[i]), round_tf32(v[i + 1]), round_tf32(v[i + 2]),
-                                                    round_tf32(v[i + 3]));
-                            }
-                            if (round_y) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) v[i] = round_tf32(v[i]);
-                            }
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4)
-                                *reinterpret_cast<float4 *>(p.y + off + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                if (co0 + i < p.Cout) {
-                                    float o = v[i];
-                                    if (p.residual) o += __ldg(p.residual + off + i);
-                                    if (p.y_tf32) p.y_tf32[off + i] = round_tf32(o);
-                                    p.y[off + i] = round_y ? round_tf32(o) : o;
-                                }
-                            }
-                        }
-                    } else {
-                        // out[n, 2*oy+i, 2*ox+j, cq] = conv[n, oy, ox, 4*cq + 2*i + j]
-                        const int H2 = p.H * 2, W2 = p.W * 2;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int co = co0 + i;
-                            const int cq = co >> 2, si = (co >> 1) & 1, sj = co & 1;
-                            const size_t o2 = (((size_t)n * H2 + 2 * oy + si) * W2 + 2 * ox + sj) * p.y_pitch + p.y_coff + cq;
-                            if (p.y_tf32) p.y_tf32[o2] = round_tf32(v[i]);
-                            p.y[o2] = round_y ? round_tf32(v[i]) : v[i];
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
-            acc ^= 1u;
-            if (acc == 0) acc_phase ^= 1u;
-        }
+        epilogue_loop(p, tmem_base, tfull_bar(0), tempty_bar(0), warp, lane, blockIdx.x, gridDim.x, p.total_tiles, -1);
     }
 
     tc_fence_before();
@@ -353,6 +362,136 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
     (void)s_bias;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel v2 for the 3x3 layers: weights resident in shared memory, one halo load per filter COLUMN.
+//
+// v1 re-stages a shifted 128-pixel window (32 KB) plus a 16 KB weight slab for each of the 9 taps:
+// 432 KB of L2 -> smem traffic per 128-pixel tile, which (at the ~51 B/clk/SM the TMA path sustains)
+// caps it near 27 % of the TF32 pipe.  Here
+//   * the 9 x 2 weight slabs of this CTA's Cout tile (144 KB) are loaded ONCE per CTA;
+//   * for each dx in {0,1,2} and K-half, ONE box of (8 + 2d) rows x 16 pixels x 32 channels is staged
+//     (x origin shifted by (dx-1)*d): the three dy taps of that column are the same buffer read at row
+//     offsets dy*d*16 pixels = dy*d*2048 B -- multiples of the 1024 B swizzle atom, so plain UMMA
+//     descriptors work without base-offset tricks;
+//   -> 6 loads of 20 KB (d=1) per tile = 120 KB: 3.6x less staging traffic, 12 MMAs per load.
+// Accumulation order per output element: (dx, K-half, dy, k-step) -- fixed, position independent.
+// ---------------------------------------------------------------------------------------------
+constexpr int W_RES_BYTES = 9 * 2 * B_HALF;       // 147456
+
+__global__ void __launch_bounds__(THREADS, 1)
+conv3x3_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                          const Params p, const int n_stages, const int a_bytes, const int ptiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // [weights 144 KB][A stages n_stages * a_bytes][barriers]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + W_RES_BYTES + n_stages * a_bytes);
+    // bars[0..3] full, [4..7] empty, [8..9] tmem_full, [10..11] tmem_empty, [12] weights
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 13);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t w_base = smem_u32(smem);
+    const uint32_t a_base = w_base + W_RES_BYTES;
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+    const uint32_t tfull0 = bar_base + 8u * 8, tempty0 = bar_base + 8u * 10, wbar = bar_base + 8u * 12;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull0 + 8u * a, 1);
+            mbar_init(tempty0 + 8u * a, 4);
+        }
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int d = p.dilation;
+    const int ct = blockIdx.y;                        // this CTA's Cout tile (weights stay resident)
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(wbar, W_RES_BYTES);
+            for (int slab = 0; slab < 18; ++slab)     // slab = tap*2 + K-half; rows [slab][cout_rows]
+                tma_load_2d(w_base + slab * B_HALF, &map_w, wbar, 0, slab * p.cout_rows + ct * 64);
+        }
+        uint32_t stage = 0, phase = 0;
+        for (int t = blockIdx.x; t < ptiles; t += gridDim.x) {
+            int q = t;
+            const int tx = q % p.tiles_x; q /= p.tiles_x;
+            const int ty = q % p.tiles_y; q /= p.tiles_y;
+            const int n = q;
+            for (int unit = 0; unit < 6; ++unit) {    // unit = dx*2 + K-half
+                if (lane == 0) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_expect_tx(full_bar(stage), a_bytes);
+                    tma_load_4d(a_base + stage * a_bytes, &map_x, full_bar(stage), (unit & 1) * 32,
+                                tx * TW + ((unit >> 1) - 1) * d, ty * TH - d, n);
+                }
+                __syncwarp();
+                if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        uint32_t stage = 0, phase = 0;
+        uint32_t acc = 0, acc_phase = 0;
+        if (lane == 0) mbar_wait(wbar, 0);
+        __syncwarp();
+        for (int t = blockIdx.x; t < ptiles; t += gridDim.x) {
+            if (lane == 0) {
+                mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);
+                tc_fence_after();
+            }
+            __syncwarp();
+            const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+            for (int unit = 0; unit < 6; ++unit) {
+                if (lane == 0) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const int dx = unit >> 1, kh = unit & 1;
+                    const uint32_t a0 = a_base + stage * a_bytes;
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const uint64_t da = make_desc(a0 + dy * d * (TW * 128));           // dy*d rows of 16 px
+                        const uint64_t db = make_desc(w_base + ((dy * 3 + dx) * 2 + kh) * B_HALF);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_tf32(d_tmem, da + 2u * k, db + 2u * k, IDESC_TF32, (unit | dy | k) != 0 ? 1u : 0u);
+                    }
+                    mma_commit(empty_bar(stage));
+                    if (unit == 5) mma_commit(tfull0 + 8u * acc);
+                }
+                __syncwarp();
+                if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1u; }
+            }
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    } else {
+        epilogue_loop(p, tmem_base, tfull0, tempty0, warp, lane, blockIdx.x, gridDim.x, ptiles, ct);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
 }
 
 // ---- host side ------------------------------------------------------------------------------
@@ -395,12 +534,20 @@ int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st) {
     EncodeTiledFn encode = get_encode_fn();
     L3C_REQUIRE(encode != nullptr, "l3c_conv2d: cuTensorMapEncodeTiled is not available from the driver");
 
+    // kernel v2 (weights resident, one halo load per filter column) for the 3x3 layers
+    const int d = p.dilation;
+    const int a_rows = TH + 2 * d;
+    const int a_bytes = a_rows * TW * 128;
+    int n_stages = (227 * 1024 - 1024 - 512 - W_RES_BYTES) / a_bytes;
+    if (n_stages > 4) n_stages = 4;
+    const bool use_v2 = k3 && a_rows <= 256 && n_stages >= 2;
+
     alignas(64) CUtensorMap map_x, map_w;
     {
         cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
         cuuint64_t strides[3] = {(cuuint64_t)p.x_pitch * 4, (cuuint64_t)p.W * p.x_pitch * 4,
                                  (cuuint64_t)p.H * p.W * p.x_pitch * 4};
-        cuuint32_t box[4] = {32, TW, TH, 1};
+        cuuint32_t box[4] = {32, TW, (cuuint32_t)(use_v2 ? a_rows : TH), 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(p.x), dims, strides, box,
                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -443,7 +590,20 @@ int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st) {
         L3C_CUDA(cudaGetDevice(&dev));
         L3C_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         L3C_CUDA(cudaFuncSetAttribute(conv3x3_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        L3C_CUDA(cudaFuncSetAttribute(conv3x3_tcgen05_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024));
         configured = true;
+    }
+    if (use_v2) {
+        const int ptiles = p.N * q.tiles_x * q.tiles_y;
+        int per_ct = n_sm / cout_tiles;
+        if (per_ct < 1) per_ct = 1;
+        if (per_ct > ptiles) per_ct = ptiles;
+        const int smem_bytes = W_RES_BYTES + n_stages * a_bytes + 1024 + 512;
+        conv3x3_tcgen05_v2_kernel<<<dim3(per_ct, cout_tiles), THREADS, smem_bytes, st>>>(map_x, map_w, q, n_stages,
+                                                                                       a_bytes, ptiles);
+        L3C_LAUNCH_CHECK("conv3x3_tcgen05_v2_kernel");
+        return L3C_OK;
     }
     const int grid = q.total_tiles < n_sm ? q.total_tiles : n_sm;      // persistent: one CTA per SM
     conv3x3_tcgen05_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(map_x, map_w, q);

@@ -424,17 +424,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!done);
 }
 
-// Estimate of count = ((value - low + 1) * 2^16 - 1) / span (torchac.cpp:327), accurate to +-1.
-// The decoder does not correct it up front: it searches with the estimate and then VERIFIES the
-// interval it found against the exact integer condition  c_lo*span <= num < c_hi*span  (both products
-// are needed for the state update anyway); a miss (estimate off by one AND a CDF entry exactly at the
-// boundary) re-runs the search with the neighbouring count.
-__device__ __forceinline__ uint32_t estimate_count(uint32_t dv, uint32_t r) {
+// count = ((value - low + 1) * 2^16 - 1) / span, exact, for value in [low, high]  (torchac.cpp:327):
+// float estimate (within 1 of the quotient) + one 64-bit integer correction, no division.
+// (Searching with the raw estimate and verifying the found interval afterwards was measured slower.)
+__device__ __forceinline__ uint32_t exact_count(uint32_t dv, uint32_t r) {
+    const uint64_t num = ((uint64_t)dv << 16) | 0xFFFFull;           // (dv+1)*65536 - 1
     const float x = __uint2float_rn(dv) + 1.0f;
     const float y = __uint2float_rn(r) + 1.0f;
     float inv;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(y));
-    return __float2uint_rz(x * inv * 65536.0f);                      // may be 65536 when dv == r
+    uint32_t q = __float2uint_rz(x * inv * 65536.0f);                // may be 65536 when dv == r
+    const uint64_t prod = (uint64_t)q * r + q;                       // q * span
+    const uint64_t span = (uint64_t)r + 1ull;
+    q = q - (prod > num ? 1u : 0u) + ((prod <= num && num - prod >= span) ? 1u : 0u);
+    return q;
 }
 
 __global__ void __launch_bounds__(64)
@@ -571,48 +574,27 @@ ac_decode256_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams,
                 const uint4 b = ring[g * G + d][1][lane];
                 const uint32_t r = cs.high - cs.low;
                 const uint32_t dv = cs.value - cs.low;
-                const bool foreign = dv > r;                                  // corrupt / foreign input only
-                uint32_t q = foreign ? foreign_count16(cs.value, cs.low, r) : min(estimate_count(dv, r), 65535u);
-                const uint64_t num = ((uint64_t)dv << 16) | 0xFFFFull;        // (dv+1)*2^16 - 1
-                uint32_t top;
-                uint64_t p_hi, p_lo;
-                for (;;) {
-                    const uint32_t thr = (q << 16) | 0xFFFFu;
-                    // rows are sorted: the last proposal with cdf[m] <= count is the numerically largest
-                    uint32_t best = (lane == 0) ? a.x : 0u;                   // symbol 0 is the floor
-                    best = (a.x <= thr) ? a.x : best;
-                    best = (a.y <= thr) ? a.y : best;
-                    best = (a.z <= thr) ? a.z : best;
-                    best = (a.w <= thr) ? a.w : best;
-                    best = (b.x <= thr) ? b.x : best;
-                    best = (b.y <= thr) ? b.y : best;
-                    best = (b.z <= thr) ? b.z : best;
-                    best = (b.w <= thr) ? b.w : best;
-                    top = __reduce_max_sync(FULL, best);
-                    const uint32_t c_lo = top >> 16;
-                    const uint32_t c_hi = (top & 0xFFFFu) + 1u;
-                    p_hi = (uint64_t)r * c_hi + c_hi;                         // c_hi * span
-                    p_lo = (uint64_t)r * c_lo + c_lo;                         // c_lo * span
-                    if (foreign) break;
-                    // exact check of  c_lo <= count < c_hi  (c_lo > count can also mean "below the floor
-                    // of the row": then symbol 0 is right and lowering q cannot change the answer)
-                    if (__builtin_expect(p_hi <= num, 0)) { q += 1u; continue; }
-                    if (__builtin_expect(p_lo > num && q > 0u, 0)) {
-                        // either the estimate is one too high with an entry exactly on the boundary, or
-                        // the value is below the first entry (then q-1 finds the same floor symbol)
-                        const uint32_t thr2 = ((q - 1u) << 16) | 0xFFFFu;
-                        uint32_t b2 = (lane == 0) ? a.x : 0u;
-                        b2 = (a.x <= thr2) ? a.x : b2; b2 = (a.y <= thr2) ? a.y : b2;
-                        b2 = (a.z <= thr2) ? a.z : b2; b2 = (a.w <= thr2) ? a.w : b2;
-                        b2 = (b.x <= thr2) ? b.x : b2; b2 = (b.y <= thr2) ? b.y : b2;
-                        b2 = (b.z <= thr2) ? b.z : b2; b2 = (b.w <= thr2) ? b.w : b2;
-                        const uint32_t top2 = __reduce_max_sync(FULL, b2);
-                        if (top2 != top) { q -= 1u; continue; }
-                    }
-                    break;
-                }
+                uint32_t q;
+                if (__builtin_expect(dv > r, 0)) q = foreign_count16(cs.value, cs.low, r);
+                else q = exact_count(dv, r);
+                const uint32_t thr = (q << 16) | 0xFFFFu;
+                // rows are sorted: the last proposal with cdf[m] <= count is the numerically largest
+                uint32_t best = (lane == 0) ? a.x : 0u;                       // symbol 0 is the floor
+                best = (a.x <= thr) ? a.x : best;
+                best = (a.y <= thr) ? a.y : best;
+                best = (a.z <= thr) ? a.z : best;
+                best = (a.w <= thr) ? a.w : best;
+                best = (b.x <= thr) ? b.x : best;
+                best = (b.y <= thr) ? b.y : best;
+                best = (b.z <= thr) ? b.z : best;
+                best = (b.w <= thr) ? b.w : best;
+                const uint32_t top = __reduce_max_sync(FULL, best);
                 if (lane == 0) tops[g * G + d] = top;
                 if (i != n - 1) {                                             // torchac.cpp:335-337
+                    const uint32_t c_lo = top >> 16;
+                    const uint32_t c_hi = (top & 0xFFFFu) + 1u;
+                    const uint64_t p_hi = (uint64_t)r * c_hi + c_hi;
+                    const uint64_t p_lo = (uint64_t)r * c_lo + c_lo;
                     const uint32_t high = cs.low - 1u + (uint32_t)(p_hi >> 16);
                     const uint32_t low = cs.low + (uint32_t)(p_lo >> 16);
                     const uint32_t k = (uint32_t)__clz((int)(low ^ high));
