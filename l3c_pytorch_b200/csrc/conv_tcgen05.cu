@@ -151,9 +151,80 @@ struct Params {
     int cout_rows;   // rows per (tap, K-half) slab of the weight image = cout_tiles * 64
 };
 
-// 4-warp epilogue shared by both kernels: TMEM -> registers -> bias / ReLU / residual / TF32 twin ->
-// global (NHWC, channel slice, or PixelShuffle(2) addressing).  Tile t of this CTA's sequence
-// t0, t0+tstride, ... ; `ct_fixed` >= 0 pins the Cout tile (kernel v2), else it is decoded from t.
+// Epilogue of one 128-pixel x 64-channel accumulator (this thread = one pixel row of the tile):
+// TMEM -> registers -> bias / ReLU / residual / TF32 twin -> global (NHWC, channel slice, or
+// PixelShuffle(2) addressing).
+__device__ __forceinline__ void epilogue_tile(const Params &p, uint32_t taddr, int ct, int n, int oy, int ox,
+                                              bool inside, bool relu, bool shuffle, bool round_y) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        const int co0 = ct * 64 + c0;
+        if (inside && co0 < p.Cout) {
+            const float4 *bp = reinterpret_cast<const float4 *>(p.bias + co0);   // padded to cout_rows, 64 B aligned
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 b = __ldg(bp + (i >> 2));
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+            }
+            if (relu) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (!shuffle) {
+                const size_t off = (((size_t)n * p.H + oy) * p.W + ox) * p.y_pitch + p.y_coff + co0;
+                const bool vec = (((p.y_pitch | p.y_coff) & 3) == 0) && (co0 + 16 <= p.Cout);
+                if (vec) {
+                    if (p.residual) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 r = __ldg(reinterpret_cast<const float4 *>(p.residual + off + i));
+                            v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
+                        }
+                    }
+                    if (p.y_tf32) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4 *>(p.y_tf32 + off + i) =
+                                make_float4(round_tf32(v[i]), round_tf32(v[i + 1]), round_tf32(v[i + 2]),
+                                            round_tf32(v[i + 3]));
+                    }
+                    if (round_y) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = round_tf32(v[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4 *>(p.y + off + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        if (co0 + i < p.Cout) {
+                            float o = v[i];
+                            if (p.residual) o += __ldg(p.residual + off + i);
+                            if (p.y_tf32) p.y_tf32[off + i] = round_tf32(o);
+                            p.y[off + i] = round_y ? round_tf32(o) : o;
+                        }
+                    }
+                }
+            } else {
+                // out[n, 2*oy+i, 2*ox+j, cq] = conv[n, oy, ox, 4*cq + 2*i + j]
+                const int H2 = p.H * 2, W2 = p.W * 2;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int co = co0 + i;
+                    const int cq = co >> 2, si = (co >> 1) & 1, sj = co & 1;
+                    const size_t o2 = (((size_t)n * H2 + 2 * oy + si) * W2 + 2 * ox + sj) * p.y_pitch + p.y_coff + cq;
+                    if (p.y_tf32) p.y_tf32[o2] = round_tf32(v[i]);
+                    p.y[o2] = round_y ? round_tf32(v[i]) : v[i];
+                }
+            }
+        }
+    }
+}
+
+// 4-warp epilogue loop of kernel v1: tile t of this CTA's sequence t0, t0+tstride, ...
 __device__ __forceinline__ void epilogue_loop(const Params &p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                               int warp, int lane, int t0, int tstride, int t_end, int ct_fixed) {
     const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 are this warp's
@@ -175,67 +246,7 @@ __device__ __forceinline__ void epilogue_loop(const Params &p, uint32_t tmem_bas
         mbar_wait(tfull0 + 8u * acc, acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 16) {
-            float v[16];
-            tmem_ld16(taddr + c0, v);
-            const int co0 = ct * 64 + c0;
-            if (inside && co0 < p.Cout) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    v[i] += __ldg(p.bias + co0 + i);          // bias is padded to cout_rows
-                    if (relu) v[i] = fmaxf(v[i], 0.f);
-                }
-                if (!shuffle) {
-                    const size_t off = (((size_t)n * p.H + oy) * p.W + ox) * p.y_pitch + p.y_coff + co0;
-                    const bool vec = (((p.y_pitch | p.y_coff) & 3) == 0) && (co0 + 16 <= p.Cout);
-                    if (vec) {
-                        if (p.residual) {
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4) {
-                                const float4 r = __ldg(reinterpret_cast<const float4 *>(p.residual + off + i));
-                                v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
-                            }
-                        }
-                        if (p.y_tf32) {
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4)
-                                *reinterpret_cast<float4 *>(p.y_tf32 + off + i) =
-                                    make_float4(round_tf32(v[i]), round_tf32(v[i + 1]), round_tf32(v[i + 2]),
-                                                round_tf32(v[i + 3]));
-                        }
-                        if (round_y) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = round_tf32(v[i]);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4 *>(p.y + off + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            if (co0 + i < p.Cout) {
-                                float o = v[i];
-                                if (p.residual) o += __ldg(p.residual + off + i);
-                                if (p.y_tf32) p.y_tf32[off + i] = round_tf32(o);
-                                p.y[off + i] = round_y ? round_tf32(o) : o;
-                            }
-                        }
-                    }
-                } else {
-                    // out[n, 2*oy+i, 2*ox+j, cq] = conv[n, oy, ox, 4*cq + 2*i + j]
-                    const int H2 = p.H * 2, W2 = p.W * 2;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int co = co0 + i;
-                        const int cq = co >> 2, si = (co >> 1) & 1, sj = co & 1;
-                        const size_t o2 = (((size_t)n * H2 + 2 * oy + si) * W2 + 2 * ox + sj) * p.y_pitch + p.y_coff + cq;
-                        if (p.y_tf32) p.y_tf32[o2] = round_tf32(v[i]);
-                        p.y[o2] = round_y ? round_tf32(v[i]) : v[i];
-                    }
-                }
-            }
-        }
+        epilogue_tile(p, taddr, ct, n, oy, ox, inside, relu, shuffle, round_y);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
@@ -379,41 +390,48 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
 // Accumulation order per output element: (dx, K-half, dy, k-step) -- fixed, position independent.
 // ---------------------------------------------------------------------------------------------
 constexpr int W_RES_BYTES = 9 * 2 * B_HALF;       // 147456
+constexpr int V2_PIPES = 2;                       // independent (TMA producer, MMA issuer) pairs
+constexpr int V2_THREADS = 32 * (2 * V2_PIPES + 4);
+constexpr int V2_TMEM_COLS = 256;                 // 2 pipes x 2 accumulators x 64 columns
 
-__global__ void __launch_bounds__(THREADS, 1)
+// ncu on kernel v1 (profiles/r01): the tensor pipe is busy 30 % of the time although L2 staging was
+// cut 3.6x -- the limiter is the ISSUE of the MMAs: with N = 64 one tcgen05.mma is only 32 cycles of
+// tensor work, while the single issuing thread needs ~25 SASS instructions (ELECT, five
+// R2UR.BROADCAST, descriptor adds ...) ~ 100 cycles per MMA.  v2 therefore runs TWO issuer threads
+// (on different warps / schedulers), each with its own producer warp, smem stages and pair of TMEM
+// accumulators, working on alternate tiles; every output element is still accumulated by exactly one
+// issuer in the fixed order (dx, K-half, dy, k-step), so results stay bit-reproducible.
+__global__ void __launch_bounds__(V2_THREADS, 1)
 conv3x3_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                           const Params p, const int n_stages, const int a_bytes, const int ptiles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    // [weights 144 KB][A stages n_stages * a_bytes][barriers]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + W_RES_BYTES + n_stages * a_bytes);
-    // bars[0..3] full, [4..7] empty, [8..9] tmem_full, [10..11] tmem_empty, [12] weights
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 13);
+    // [weights 144 KB][pipe 0 stages][pipe 1 stages][barriers]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + W_RES_BYTES + V2_PIPES * n_stages * a_bytes);
+    // per pipe k (base 8k): full[0..1], empty[2..3], tfull[4..5], tempty[6..7]; bars[16] = weights
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 17);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t w_base = smem_u32(smem);
-    const uint32_t a_base = w_base + W_RES_BYTES;
     const uint32_t bar_base = smem_u32(bars);
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
-    const uint32_t tfull0 = bar_base + 8u * 8, tempty0 = bar_base + 8u * 10, wbar = bar_base + 8u * 12;
+    const uint32_t wbar = bar_base + 8u * 16;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 4; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(tfull0 + 8u * a, 1);
-            mbar_init(tempty0 + 8u * a, 4);
+        for (int k = 0; k < V2_PIPES; ++k) {
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(bar_base + 8u * (8 * k + s), 1);          // full
+                mbar_init(bar_base + 8u * (8 * k + 2 + s), 1);      // empty
+                mbar_init(bar_base + 8u * (8 * k + 4 + s), 1);      // tmem full
+                mbar_init(bar_base + 8u * (8 * k + 6 + s), 4);      // tmem empty (one arrival per epilogue warp)
+            }
         }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    if (warp == V2_PIPES) tmem_alloc(smem_u32(tmem_slot), V2_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -422,46 +440,53 @@ conv3x3_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
     const int d = p.dilation;
     const int ct = blockIdx.y;                        // this CTA's Cout tile (weights stay resident)
 
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+    if (warp < V2_PIPES) {
+        // ===================== TMA producer of pipe `warp` =====================
+        const int k = warp;
+        const uint32_t a_base = w_base + W_RES_BYTES + k * n_stages * a_bytes;
+        const uint32_t full0 = bar_base + 8u * (8 * k), empty0 = bar_base + 8u * (8 * k + 2);
+        if (k == 0 && lane == 0) {
             mbar_expect_tx(wbar, W_RES_BYTES);
             for (int slab = 0; slab < 18; ++slab)     // slab = tap*2 + K-half; rows [slab][cout_rows]
                 tma_load_2d(w_base + slab * B_HALF, &map_w, wbar, 0, slab * p.cout_rows + ct * 64);
         }
         uint32_t stage = 0, phase = 0;
-        for (int t = blockIdx.x; t < ptiles; t += gridDim.x) {
+        for (int t = blockIdx.x + k * gridDim.x; t < ptiles; t += V2_PIPES * gridDim.x) {
             int q = t;
             const int tx = q % p.tiles_x; q /= p.tiles_x;
             const int ty = q % p.tiles_y; q /= p.tiles_y;
             const int n = q;
             for (int unit = 0; unit < 6; ++unit) {    // unit = dx*2 + K-half
                 if (lane == 0) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_expect_tx(full_bar(stage), a_bytes);
-                    tma_load_4d(a_base + stage * a_bytes, &map_x, full_bar(stage), (unit & 1) * 32,
+                    mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+                    mbar_expect_tx(full0 + 8u * stage, a_bytes);
+                    tma_load_4d(a_base + stage * a_bytes, &map_x, full0 + 8u * stage, (unit & 1) * 32,
                                 tx * TW + ((unit >> 1) - 1) * d, ty * TH - d, n);
                 }
                 __syncwarp();
                 if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp < 2 * V2_PIPES) {
+        // ===================== MMA issuer of pipe `warp - V2_PIPES` =====================
+        const int k = warp - V2_PIPES;
+        const uint32_t a_base = w_base + W_RES_BYTES + k * n_stages * a_bytes;
+        const uint32_t full0 = bar_base + 8u * (8 * k), empty0 = bar_base + 8u * (8 * k + 2);
+        const uint32_t tfull0 = bar_base + 8u * (8 * k + 4), tempty0 = bar_base + 8u * (8 * k + 6);
         uint32_t stage = 0, phase = 0;
         uint32_t acc = 0, acc_phase = 0;
         if (lane == 0) mbar_wait(wbar, 0);
         __syncwarp();
-        for (int t = blockIdx.x; t < ptiles; t += gridDim.x) {
+        for (int t = blockIdx.x + k * gridDim.x; t < ptiles; t += V2_PIPES * gridDim.x) {
             if (lane == 0) {
                 mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);
                 tc_fence_after();
             }
             __syncwarp();
-            const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+            const uint32_t d_tmem = tmem_base + (k * 2 + acc) * ACC_COLS;
             for (int unit = 0; unit < 6; ++unit) {
                 if (lane == 0) {
-                    mbar_wait(full_bar(stage), phase);
+                    mbar_wait(full0 + 8u * stage, phase);
                     tc_fence_after();
                     const int dx = unit >> 1, kh = unit & 1;
                     const uint32_t a0 = a_base + stage * a_bytes;
@@ -470,10 +495,10 @@ conv3x3_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
                         const uint64_t da = make_desc(a0 + dy * d * (TW * 128));           // dy*d rows of 16 px
                         const uint64_t db = make_desc(w_base + ((dy * 3 + dx) * 2 + kh) * B_HALF);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            mma_tf32(d_tmem, da + 2u * k, db + 2u * k, IDESC_TF32, (unit | dy | k) != 0 ? 1u : 0u);
+                        for (int kk = 0; kk < 4; ++kk)
+                            mma_tf32(d_tmem, da + 2u * kk, db + 2u * kk, IDESC_TF32, (unit | dy | kk) != 0 ? 1u : 0u);
                     }
-                    mma_commit(empty_bar(stage));
+                    mma_commit(empty0 + 8u * stage);
                     if (unit == 5) mma_commit(tfull0 + 8u * acc);
                 }
                 __syncwarp();
@@ -483,14 +508,40 @@ conv3x3_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
             if (acc == 0) acc_phase ^= 1u;
         }
     } else {
-        epilogue_loop(p, tmem_base, tfull0, tempty0, warp, lane, blockIdx.x, gridDim.x, ptiles, ct);
+        // ===================== epilogue: tiles in sequence order, alternating pipes =====================
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;
+        const bool relu = (p.flags & L3C_CONV_RELU) != 0;
+        const bool shuffle = (p.flags & L3C_CONV_PIXEL_SHUFFLE2) != 0;
+        const bool round_y = (p.flags & L3C_CONV_ROUND_TF32) != 0;
+        int j = 0;
+        for (int t = blockIdx.x; t < ptiles; t += gridDim.x, ++j) {
+            const int k = j % V2_PIPES;
+            const uint32_t acc = (uint32_t)(j / V2_PIPES) & 1u;
+            const uint32_t acc_phase = (uint32_t)(j / (2 * V2_PIPES)) & 1u;
+            const uint32_t tfull = bar_base + 8u * (8 * k + 4 + acc), tempty = bar_base + 8u * (8 * k + 6 + acc);
+            int q = t;
+            const int tx = q % p.tiles_x; q /= p.tiles_x;
+            const int ty = q % p.tiles_y; q /= p.tiles_y;
+            const int n = q;
+            const int oy = ty * TH + (m >> 4);
+            const int ox = tx * TW + (m & 15);
+            const bool inside = (oy < p.H) && (ox < p.W);
+            mbar_wait(tfull, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (k * 2 + acc) * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+            epilogue_tile(p, taddr, ct, n, oy, ox, inside, relu, shuffle, round_y);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+        }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == V2_PIPES) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc(tmem_base, V2_TMEM_COLS);
     }
 }
 
@@ -538,9 +589,9 @@ int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st) {
     const int d = p.dilation;
     const int a_rows = TH + 2 * d;
     const int a_bytes = a_rows * TW * 128;
-    int n_stages = (227 * 1024 - 1024 - 512 - W_RES_BYTES) / a_bytes;
-    if (n_stages > 4) n_stages = 4;
-    const bool use_v2 = k3 && a_rows <= 256 && n_stages >= 2;
+    int n_stages = (227 * 1024 - 1024 - 512 - W_RES_BYTES) / (V2_PIPES * a_bytes);      // per pipe
+    if (n_stages > 2) n_stages = 2;
+    const bool use_v2 = k3 && a_rows <= 256 && n_stages >= 1;
 
     alignas(64) CUtensorMap map_x, map_w;
     {
@@ -599,9 +650,9 @@ int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st) {
         int per_ct = n_sm / cout_tiles;
         if (per_ct < 1) per_ct = 1;
         if (per_ct > ptiles) per_ct = ptiles;
-        const int smem_bytes = W_RES_BYTES + n_stages * a_bytes + 1024 + 512;
-        conv3x3_tcgen05_v2_kernel<<<dim3(per_ct, cout_tiles), THREADS, smem_bytes, st>>>(map_x, map_w, q, n_stages,
-                                                                                       a_bytes, ptiles);
+        const int smem_bytes = W_RES_BYTES + V2_PIPES * n_stages * a_bytes + 1024 + 512;
+        conv3x3_tcgen05_v2_kernel<<<dim3(per_ct, cout_tiles), V2_THREADS, smem_bytes, st>>>(map_x, map_w, q, n_stages,
+                                                                                          a_bytes, ptiles);
         L3C_LAUNCH_CHECK("conv3x3_tcgen05_v2_kernel");
         return L3C_OK;
     }
