@@ -154,19 +154,27 @@ struct Params {
 // Epilogue of one 128-pixel x 64-channel accumulator (this thread = one pixel row of the tile):
 // TMEM -> registers -> bias / ReLU / residual / TF32 twin -> global (NHWC, channel slice, or
 // PixelShuffle(2) addressing).
+template <int NCHUNK>
 __device__ __forceinline__ void epilogue_tile(const Params &p, uint32_t taddr, int ct, int n, int oy, int ox,
-                                              bool inside, bool relu, bool shuffle, bool round_y) {
-#pragma unroll 1
-    for (int c0 = 0; c0 < 64; c0 += 16) {
+                                              bool inside, bool relu, bool shuffle, bool round_y, int cbeg,
+                                              const float *bias_regs /* NCHUNK*16 preloaded values or null */) {
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int c0 = cbeg + ch * 16;
         float v[16];
         tmem_ld16(taddr + c0, v);
         const int co0 = ct * 64 + c0;
         if (inside && co0 < p.Cout) {
-            const float4 *bp = reinterpret_cast<const float4 *>(p.bias + co0);   // padded to cout_rows, 64 B aligned
+            if (bias_regs) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-                const float4 b = __ldg(bp + (i >> 2));
-                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                for (int i = 0; i < 16; ++i) v[i] += bias_regs[ch * 16 + i];
+            } else {
+                const float4 *bp = reinterpret_cast<const float4 *>(p.bias + co0);   // padded, 64 B aligned
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 b = __ldg(bp + (i >> 2));
+                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                }
             }
             if (relu) {
 #pragma unroll
@@ -246,7 +254,7 @@ __device__ __forceinline__ void epilogue_loop(const Params &p, uint32_t tmem_bas
         mbar_wait(tfull0 + 8u * acc, acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
-        epilogue_tile(p, taddr, ct, n, oy, ox, inside, relu, shuffle, round_y);
+        epilogue_tile<4>(p, taddr, ct, n, oy, ox, inside, relu, shuffle, round_y, 0, nullptr);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
@@ -391,7 +399,8 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
 // ---------------------------------------------------------------------------------------------
 constexpr int W_RES_BYTES = 9 * 2 * B_HALF;       // 147456
 constexpr int V2_PIPES = 2;                       // independent (TMA producer, MMA issuer) pairs
-constexpr int V2_THREADS = 32 * (2 * V2_PIPES + 4);
+constexpr int V2_EPI_WARPS = 8;                   // two warps per TMEM lane quarter, 32 columns each
+constexpr int V2_THREADS = 32 * (2 * V2_PIPES + V2_EPI_WARPS);
 constexpr int V2_TMEM_COLS = 256;                 // 2 pipes x 2 accumulators x 64 columns
 
 // ncu on kernel v1 (profiles/r01): the tensor pipe is busy 30 % of the time although L2 staging was
@@ -423,7 +432,7 @@ conv3x3_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
                 mbar_init(bar_base + 8u * (8 * k + s), 1);          // full
                 mbar_init(bar_base + 8u * (8 * k + 2 + s), 1);      // empty
                 mbar_init(bar_base + 8u * (8 * k + 4 + s), 1);      // tmem full
-                mbar_init(bar_base + 8u * (8 * k + 6 + s), 4);      // tmem empty (one arrival per epilogue warp)
+                mbar_init(bar_base + 8u * (8 * k + 6 + s), V2_EPI_WARPS);   // tmem empty: one arrival per epilogue warp
             }
         }
         mbar_init(wbar, 1);
@@ -509,11 +518,21 @@ conv3x3_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
         }
     } else {
         // ===================== epilogue: tiles in sequence order, alternating pipes =====================
+        // warp e of the 8 epilogue warps: TMEM lane quarter = warp id % 4 (hardware rule), column half
+        // = e / 4.  The 32 bias values of this half are loaded once (this CTA's Cout tile is fixed).
+        const int e = warp - 2 * V2_PIPES;
         const int quarter = warp & 3;
+        const int cbeg = (e >> 2) * 32;
         const int m = quarter * 32 + lane;
         const bool relu = (p.flags & L3C_CONV_RELU) != 0;
         const bool shuffle = (p.flags & L3C_CONV_PIXEL_SHUFFLE2) != 0;
         const bool round_y = (p.flags & L3C_CONV_ROUND_TF32) != 0;
+        float bias_regs[32];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + ct * 64 + cbeg + i));
+            bias_regs[i] = b.x; bias_regs[i + 1] = b.y; bias_regs[i + 2] = b.z; bias_regs[i + 3] = b.w;
+        }
         int j = 0;
         for (int t = blockIdx.x; t < ptiles; t += gridDim.x, ++j) {
             const int k = j % V2_PIPES;
@@ -530,7 +549,7 @@ conv3x3_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
             mbar_wait(tfull, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (k * 2 + acc) * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
-            epilogue_tile(p, taddr, ct, n, oy, ox, inside, relu, shuffle, round_y);
+            epilogue_tile<2>(p, taddr, ct, n, oy, ox, inside, relu, shuffle, round_y, cbeg, bias_regs);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty);
