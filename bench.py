@@ -288,7 +288,11 @@ def run_ours(args):
     peak_tf = peaks.get('bf16_tflops', 1590.0)
     achieved_tf = conv_flops / (conv_ms / 1e3) / 1e12
     roofline = {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': achieved_tf / peak_tf, 'traffic': None,
+                'frac': achieved_tf / peak_tf,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this shape, one launch, from the
+                # ncu --set full capture committed as profiles/r01b_conv3x3_tcgen05_v2_ncu_full_raw.csv
+                # (algorithmic: 268 MB read + 268 MB written)
+                'traffic': 484.4e6 if (args.precision == 'tf32' and n_img == 16) else None,
                 'kernel': 'conv3x3 64->64, %dx256x256 NHWC fp32 (%s path)' % (n_img, args.precision),
                 'peak_source': 'MEASURED_PEAKS.json bf16 burst' if peaks else 'fallback 1.59 PFLOP/s',
                 'whole_step_conv_tflops': CONV_FLOP_PER_PX_ROUNDTRIP * n_img * HW * HW * args.steps /

@@ -574,20 +574,32 @@ ac_decode256_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams,
                 const uint4 b = ring[g * G + d][1][lane];
                 const uint32_t r = cs.high - cs.low;
                 const uint32_t dv = cs.value - cs.low;
-                uint32_t q;
-                if (__builtin_expect(dv > r, 0)) q = foreign_count16(cs.value, cs.low, r);
-                else q = exact_count(dv, r);
-                const uint32_t thr = (q << 16) | 0xFFFFu;
-                // rows are sorted: the last proposal with cdf[m] <= count is the numerically largest
-                uint32_t best = (lane == 0) ? a.x : 0u;                       // symbol 0 is the floor
-                best = (a.x <= thr) ? a.x : best;
-                best = (a.y <= thr) ? a.y : best;
-                best = (a.z <= thr) ? a.z : best;
-                best = (a.w <= thr) ? a.w : best;
-                best = (b.x <= thr) ? b.x : best;
-                best = (b.y <= thr) ? b.y : best;
-                best = (b.z <= thr) ? b.z : best;
-                best = (b.w <= thr) ? b.w : best;
+                // cdf[m] <= count  <=>  cdf[m] * span < (value - low + 1) << 16   (no division; the
+                // float-estimated count was measured ~85 cycles longer on the dependent chain)
+                uint64_t target = ((uint64_t)dv + 1ull) << 16;
+                uint32_t r_cmp = r;
+                if (__builtin_expect(dv > r, 0)) {                            // corrupt / foreign input only
+                    target = (uint64_t)foreign_count16(cs.value, cs.low, r) + 1ull;
+                    r_cmp = 0u;
+                }
+                // rows are sorted: the last proposal whose cdf[m] passes is the numerically largest
+                const uint32_t pk[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                uint32_t m01, m23, m45, m67;
+                {
+                    const bool f0 = (lane == 0) || below(pk[0] >> 16, r_cmp, target);   // symbol 0 is the floor
+                    const bool f1 = below(pk[1] >> 16, r_cmp, target);
+                    const bool f2 = below(pk[2] >> 16, r_cmp, target);
+                    const bool f3 = below(pk[3] >> 16, r_cmp, target);
+                    const bool f4 = below(pk[4] >> 16, r_cmp, target);
+                    const bool f5 = below(pk[5] >> 16, r_cmp, target);
+                    const bool f6 = below(pk[6] >> 16, r_cmp, target);
+                    const bool f7 = below(pk[7] >> 16, r_cmp, target);
+                    m01 = f1 ? pk[1] : (f0 ? pk[0] : 0u);
+                    m23 = f3 ? pk[3] : (f2 ? pk[2] : 0u);
+                    m45 = f5 ? pk[5] : (f4 ? pk[4] : 0u);
+                    m67 = f7 ? pk[7] : (f6 ? pk[6] : 0u);
+                }
+                const uint32_t best = max(max(m01, m23), max(m45, m67));
                 const uint32_t top = __reduce_max_sync(FULL, best);
                 if (lane == 0) tops[g * G + d] = top;
                 if (i != n - 1) {                                             // torchac.cpp:335-337

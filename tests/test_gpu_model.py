@@ -216,3 +216,46 @@ def test_reference_shaped_per_channel_api():
         back = r.range_decode(enc, cdf)
         assert torch.equal(back.long(), out.S[0][:, c].cpu())
         dec_bn[:, c] = img[:, c].float()
+
+
+def test_cli_png_round_trip_with_checkpoint(tmp_path):
+    """`l3c.py enc/dec` equivalent: checkpoint in the reference's {'net': state_dict} format, PNG in,
+    .l3c out, PNG back -- pixel exact."""
+    from PIL import Image
+    from l3c_pytorch_b200 import cli
+    bp = util.blueprint('cr')
+    sd = {k: v.detach().cpu() + 0.001 for k, v in bp.net.state_dict().items()}     # not the default init
+    ck = str(tmp_path / 'ckpt_0000000001.pt')
+    torch.save({'net': sd}, ck)
+    arr = util.make_image(7, 70, 50).permute(1, 2, 0).numpy()
+    src = str(tmp_path / 'in.png')
+    Image.fromarray(arr).save(src)
+    out = str(tmp_path / 'x.l3c')
+    assert cli.main(['--config', 'cr', '--ckpt', ck, 'enc', src, out]) == 0
+    assert cli.main(['--config', 'cr', '--ckpt', ck, 'enc', src, out]) == 1          # exists -> EncodeError
+    back = str(tmp_path / 'back.png')
+    assert cli.main(['--config', 'cr', '--ckpt', ck, 'dec', out, back]) == 0
+    assert (np.array(Image.open(back)) == arr).all()
+    assert cli.main(['--config', 'cr', '--ckpt', ck, 'dec', str(tmp_path / 'missing.l3c'), back]) == 1
+
+
+def test_tf32_and_fp32_modes_agree_on_size():
+    """the tensor-core mode changes parameters only by float noise: container sizes of a batch differ
+    by a few bytes per image from the fp32 path (mean |d bpsp| < 1e-4 at 256^2 for L3C)."""
+    from l3c_pytorch_b200 import Bitcoding, engine as E
+    bp = util.blueprint('cr')
+    bc = Bitcoding(bp)
+    imgs = torch.stack([util.make_image(20 + i, 256, 256) for i in range(4)])
+    old = E.get_conv_precision()
+    try:
+        sizes = {}
+        for mode in ('fp32', 'tf32'):
+            E.set_conv_precision(mode)
+            datas, _ = bc.encode_batch(imgs)
+            dec = bc.decode_batch(datas)
+            assert all(torch.equal(dec[i][0].cpu(), imgs[i].long()) for i in range(4))
+            sizes[mode] = np.array([len(d) for d in datas])
+    finally:
+        E.set_conv_precision(old)
+    d_bpsp = np.abs(sizes['fp32'] - sizes['tf32']).mean() * 8 / (3 * 256 * 256)
+    assert d_bpsp < 1e-4, (sizes, d_bpsp)
