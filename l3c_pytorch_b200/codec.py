@@ -319,5 +319,13 @@ class BatchCodec(object):
                     E.dmll_build_table(l, S, tg, C, K, dmll.L, False, -1, table)
                     E.ac_decode_streams(desc, dev, dmll.L)
             if scale > 0:
-                bn8 = E.symbols_to_values(S, dmll.values(dev), self._rgb_shift(dev))
+                bn8 = E.symbols_to_values(S, self._symbol_values(scale, dmll, dev), self._rgb_shift(dev))
         return S
+
+    def _symbol_values(self, scale, dmll, dev):
+        """Value of every symbol of bottleneck `scale`: the `levels` LUT of the quantiser that produced
+        it (nets[scale-1].enc.levels, a checkpoint parameter: net.py:123-127) so that the decoder feeds
+        its nets exactly what the encoder fed (SURVEY finding 1); plain 0..255 for the RGB baselines."""
+        if self.net._rgb:
+            return dmll.values(dev)
+        return self.net.nets[scale - 1].enc.levels.detach().float().contiguous()
