@@ -30,8 +30,6 @@
 
 namespace l3c {
 
-int conv2d_ffma(const l3c_conv_t &p, cudaStream_t st);
-
 namespace tc {
 
 constexpr int TH = 8, TW = 16;                 // 128 output pixels = UMMA M
@@ -42,7 +40,7 @@ constexpr int STAGE_BYTES = 2 * A_HALF + 2 * B_HALF;   // 48 KB per filter tap
 constexpr int THREADS = 192;                   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 constexpr int ACC_COLS = 64;
 constexpr int TMEM_COLS = 128;                 // two accumulators
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + 256 /*bias*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -272,7 +270,6 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
     // bars[0..3] full, [4..7] empty, [8..9] tmem_full, [10..11] tmem_empty
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
-    float *s_bias = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -380,7 +377,6 @@ conv3x3_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
-    (void)s_bias;
 }
 
 // ---------------------------------------------------------------------------------------------
