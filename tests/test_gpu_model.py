@@ -259,3 +259,44 @@ def test_tf32_and_fp32_modes_agree_on_size():
         E.set_conv_precision(old)
     d_bpsp = np.abs(sizes['fp32'] - sizes['tf32']).mean() * 8 / (3 * 256 * 256)
     assert d_bpsp < 1e-4, (sizes, d_bpsp)
+
+
+def test_full_size_crop_config_round_trip(tmp_path):
+    """BASELINE config 5 shape: one 3x3000x2000 image -> 4 crops of 1500x1000 padded to 1504x1000,
+    coded as one batch into .part0..3, decoded and stitched -- lossless (size-independent property)."""
+    from l3c_pytorch_b200 import Bitcoding, engine as E
+    bp = util.blueprint('cr')
+    bc = Bitcoding(bp)
+    old = E.get_conv_precision()
+    E.set_conv_precision('tf32')
+    try:
+        g = torch.Generator().manual_seed(4242)
+        img = (torch.rand(3, 3000, 2000, generator=g) * 255).round().to(torch.uint8)
+        p = str(tmp_path / 'big.l3c')
+        bpsp = bc.encode(img.long(), p)
+        parts = sorted(os.listdir(tmp_path))
+        assert parts == ['big.l3c.part%d' % i for i in range(4)]
+        head = open(str(tmp_path / parts[0]), 'rb').read()[:8]
+        assert head == bytes([0, 0, 0, 0, 2, 0, 2, 0])                  # pad (L,R,T,B) = (0,0,2,2): 1504x1000
+        assert 17.5 < bpsp < 19.0
+        dec = bc.decode(str(tmp_path / parts[0]))
+        assert dec.shape == (1, 3, 3000, 2000) and torch.equal(dec[0].cpu(), img.long())
+    finally:
+        E.set_conv_precision(old)
+
+
+def test_rgb_shared_batch32_round_trip():
+    """BASELINE config 4 shape: 32 x 3x256x256, cr_rgb_shared.cf (strict fp32 mode)."""
+    from l3c_pytorch_b200 import Bitcoding, engine as E
+    bp = util.blueprint('cr_rgb_shared')
+    bc = Bitcoding(bp)
+    old = E.get_conv_precision()
+    E.set_conv_precision('fp32')
+    try:
+        imgs = torch.stack([util.make_image(100 + i, 256, 256) for i in range(32)])
+        datas, bpsps = bc.encode_batch(imgs)
+        dec = bc.decode_batch(datas)
+        assert all(torch.equal(dec[i][0].cpu(), imgs[i].long()) for i in range(32))
+        assert abs(np.mean(bpsps) - 15.25) < 0.05
+    finally:
+        E.set_conv_precision(old)
