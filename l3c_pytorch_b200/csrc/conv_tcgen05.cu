@@ -116,6 +116,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+
+// tcgen05.ld shape 16x256b, 4 column repeats: 16 TMEM lanes x 32 columns per instruction.  Register
+// layout (the mma C-fragment layout): thread t holds, for column block j = 0..3,
+//   r[4j+0], r[4j+1] = (lane t/4    , columns 8j + 2*(t%4) + {0,1})
+//   r[4j+2], r[4j+3] = (lane t/4 + 8, same columns)
+// so the four threads of a quad own 32 contiguous bytes of one row: full-sector global stores.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float *v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu)      // start address
@@ -515,20 +533,20 @@ conv3x3_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
     } else {
         // ===================== epilogue: tiles in sequence order, alternating pipes =====================
         // warp e of the 8 epilogue warps: TMEM lane quarter = warp id % 4 (hardware rule), column half
-        // = e / 4.  The 32 bias values of this half are loaded once (this CTA's Cout tile is fixed).
+        // h = e / 4 (32 columns).  Accumulators are read with the 16x256b shape so that a quad of threads
+        // owns 32 contiguous bytes of a pixel row: every global access below moves whole 32 B sectors
+        // (the 32x32b shape made each STG.128 touch 32 half-used sectors).
         const int e = warp - 2 * V2_PIPES;
         const int quarter = warp & 3;
         const int cbeg = (e >> 2) * 32;
-        const int m = quarter * 32 + lane;
+        const int tq = lane & 3, tr = lane >> 2;              // column pair / row inside the fragment
         const bool relu = (p.flags & L3C_CONV_RELU) != 0;
         const bool shuffle = (p.flags & L3C_CONV_PIXEL_SHUFFLE2) != 0;
         const bool round_y = (p.flags & L3C_CONV_ROUND_TF32) != 0;
-        float bias_regs[32];
+        float2 bias2[4];                                      // bias of columns cbeg + 8j + 2*tq + {0,1}
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + ct * 64 + cbeg + i));
-            bias_regs[i] = b.x; bias_regs[i + 1] = b.y; bias_regs[i + 2] = b.z; bias_regs[i + 3] = b.w;
-        }
+        for (int jb = 0; jb < 4; ++jb)
+            bias2[jb] = __ldg(reinterpret_cast<const float2 *>(p.bias + ct * 64 + cbeg + 8 * jb + 2 * tq));
         int j = 0;
         for (int t = blockIdx.x; t < ptiles; t += gridDim.x, ++j) {
             const int k = j % V2_PIPES;
@@ -539,13 +557,49 @@ conv3x3_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
             const int tx = q % p.tiles_x; q /= p.tiles_x;
             const int ty = q % p.tiles_y; q /= p.tiles_y;
             const int n = q;
-            const int oy = ty * TH + (m >> 4);
-            const int ox = tx * TW + (m & 15);
-            const bool inside = (oy < p.H) && (ox < p.W);
             mbar_wait(tfull, acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (k * 2 + acc) * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
-            epilogue_tile<2>(p, taddr, ct, n, oy, ox, inside, relu, shuffle, round_y, cbeg, bias_regs);
+#pragma unroll
+            for (int lh = 0; lh < 2; ++lh) {
+                // TMEM lanes 32*quarter + 16*lh + {tr, tr+8}  <->  tile rows (pixels) of the same index
+                float v[16];
+                tmem_ld_16x256b_x4(tmem_base + (k * 2 + acc) * ACC_COLS + cbeg +
+                                       ((uint32_t)(quarter * 32 + lh * 16) << 16), v);
+                const int oy = ty * TH + 2 * quarter + lh;
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh) {
+                    const int ox = tx * TW + tr + 8 * rh;
+                    if (oy >= p.H || ox >= p.W) continue;
+                    const size_t pix = ((size_t)n * p.H + oy) * p.W + ox;
+#pragma unroll
+                    for (int jb = 0; jb < 4; ++jb) {
+                        float a = v[4 * jb + 2 * rh] + bias2[jb].x;
+                        float b = v[4 * jb + 2 * rh + 1] + bias2[jb].y;
+                        if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                        const int co = ct * 64 + cbeg + 8 * jb + 2 * tq;
+                        if (!shuffle) {
+                            const size_t off = pix * p.y_pitch + p.y_coff + co;
+                            if (p.residual) {
+                                const float2 r = __ldg(reinterpret_cast<const float2 *>(p.residual + off));
+                                a += r.x; b += r.y;
+                            }
+                            if (p.y_tf32) *reinterpret_cast<float2 *>(p.y_tf32 + off) = make_float2(round_tf32(a), round_tf32(b));
+                            if (round_y) { a = round_tf32(a); b = round_tf32(b); }
+                            *reinterpret_cast<float2 *>(p.y + off) = make_float2(a, b);
+                        } else {
+                            // out[n, 2*oy+i, 2*ox+jj, cq] = conv[n, oy, ox, 4*cq + 2*i + jj]; co is even:
+                            // (co, co+1) -> same cq and i, jj = 0 / 1 -> two horizontally adjacent pixels
+                            const int cq = co >> 2, si = (co >> 1) & 1;
+                            const size_t o2 = (((size_t)n * (2 * p.H) + 2 * oy + si) * (2 * p.W) + 2 * ox) * p.y_pitch +
+                                              p.y_coff + cq;
+                            if (p.y_tf32) { p.y_tf32[o2] = round_tf32(a); p.y_tf32[o2 + p.y_pitch] = round_tf32(b); }
+                            if (round_y) { a = round_tf32(a); b = round_tf32(b); }
+                            p.y[o2] = a;
+                            p.y[o2 + p.y_pitch] = b;
+                        }
+                    }
+                }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty);
