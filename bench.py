@@ -101,8 +101,10 @@ def cpu_roundtrip_mpx_s(n_images, hw, first_image=0):
     from l3c_pytorch_b200 import config
     from l3c_pytorch_b200.blueprint import MultiscaleBlueprint
     from oracle import model as om
-    try:        # torchrun pins OMP_NUM_THREADS=1; the CPU reference gets all host cores it may use
-        torch.set_num_threads(max(torch.get_num_threads(), len(os.sched_getaffinity(0))))
+    try:        # torchrun pins OMP_NUM_THREADS=1: give the CPU reference the physical cores it may use;
+        # otherwise keep PyTorch's own default (measured faster than one thread per SMT sibling)
+        if torch.get_num_threads() == 1:
+            torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) // 2))
     except (AttributeError, RuntimeError):
         pass
     torch.manual_seed(0)
