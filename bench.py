@@ -222,115 +222,45 @@ def run_ours(args):
     except (OSError, KeyError):
         pass
 
-    # ---- timed: device-resident.  Software pipelining across steps: the encode of step k+1 (forward
-    #      pass = tensor-core bound) runs on one CUDA stream while the decode of step k (serial range
-    #      decoder = latency bound, < 2 % of the SMs busy) runs on another; every one of the K round trips
-    #      starts and completes inside the timed region.  `sequential` below is the same loop without
-    #      overlap (encode -> decode -> next step).
-    def timed_resident(overlap):
-        cur = torch.cuda.current_stream()
-        s_enc = torch.cuda.Stream(device=dev) if overlap else cur
-        s_dec = torch.cuda.Stream(device=dev) if overlap else cur
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        keep = []
-        barrier()
-        t_w0 = time.time()
-        e0.record(cur)
-        s_enc.wait_event(e0)
-        s_dec.wait_event(e0)
-        n_launch0 = E.LAUNCHES['n']
-        for s in range(args.steps):
-            with torch.cuda.stream(s_enc):
-                blob, info = codec.encode_batch(dev_sets[s % n_sets], to_host=False)
-                done = torch.cuda.Event()
-                done.record(s_enc)
-            blob.record_stream(s_dec)
-            with torch.cuda.stream(s_dec):
-                s_dec.wait_event(done)
-                S = codec.decode_device(blob, info['stream_offsets'], info['lens'],
-                                        [(C, H, W) for (_, C, H, W) in info['shapes']])
-            keep.append((blob, S))
-        n_launch = E.LAUNCHES['n'] - n_launch0
-        for st in (s_enc, s_dec):
-            fin = torch.cuda.Event()
-            fin.record(st)
-            cur.wait_event(fin)
-        e1.record(cur)
-        barrier()
-        t_w1 = time.time()
-        ms_ = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms_, op=dist.ReduceOp.MAX)
-        last_ok = bool(torch.equal(keep[-1][1], dev_sets[(args.steps - 1) % n_sets]))
-        return float(ms_), n_launch, t_w0, t_w1, last_ok
-
-    seq_ms, _, _, _, ok_seq = timed_resident(False)
+    # ---- timed: device-resident
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    ms_total, launches_timed, t_wall0, t_wall1, ok_pipe = timed_resident(not args.no_overlap)
+    barrier()
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launches0 = E.LAUNCHES['n']
+    for s in range(args.steps):
+        S, info = step_resident(dev_sets[s % n_sets])
+    launches_timed = E.LAUNCHES['n'] - launches0
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop(t_wall0, t_wall1)
-    assert ok_seq and ok_pipe, 'round trip is not lossless'
+    ms_total = float(ms)
     px_step_global = n_global * HW * HW
     value = px_step_global * args.steps / 1e6 / (ms_total / 1e3)
-    value_seq = px_step_global * args.steps / 1e6 / (seq_ms / 1e3)
 
-    # ---- timed: end to end through the public API (host buffers, copies inside).  Same pipelining with
-    #      two host threads: one encodes batch k+1 (H2D of the images .. D2H of the containers) while the
-    #      other decodes batch k (H2D of the containers .. D2H of the decoded images).
+    # ---- timed: end to end through the public API (host buffers, copies inside)
     back, datas = step_e2e(host_sets[0])
     assert torch.equal(back, host_sets[0]), 'e2e round trip is not lossless'
-
-    def timed_e2e(overlap):
-        import queue
-        import threading
-        results = [None] * args.steps
-        barrier()
-        t0 = time.perf_counter()
-        if not overlap:
-            for s in range(args.steps):
-                results[s] = step_e2e(host_sets[s % n_sets])
-        else:
-            q = queue.Queue(maxsize=2)
-            err = []
-
-            def encoder():
-                try:
-                    torch.cuda.set_device(local_rank)
-                    with torch.cuda.stream(torch.cuda.Stream(device=dev)):
-                        for s in range(args.steps):
-                            q.put((s, bc.encode_batch(host_sets[s % n_sets])[0]))
-                except Exception as ex:            # noqa: BLE001
-                    err.append(ex)
-                finally:
-                    q.put(None)
-
-            th = threading.Thread(target=encoder)
-            th.start()
-            with torch.cuda.stream(torch.cuda.Stream(device=dev)):
-                while True:
-                    item = q.get()
-                    if item is None:
-                        break
-                    s, dts = item
-                    dec = bc.decode_batch(dts)
-                    results[s] = (torch.cat(dec, 0).to(torch.uint8).cpu(), dts)
-            th.join()
-            if err:
-                raise err[0]
-        barrier()
-        wall = time.perf_counter() - t0
-        w = torch.tensor([wall * 1e3], device=dev)
-        if world > 1:
-            dist.all_reduce(w, op=dist.ReduceOp.MAX)
-        ok = torch.equal(results[-1][0], host_sets[(args.steps - 1) % n_sets])
-        return float(w), results[-1][1], ok
-
-    e2e_seq_ms, datas, ok1 = timed_e2e(False)
-    e2e_ms, datas, ok2 = timed_e2e(not args.no_overlap)
-    assert ok1 and ok2, 'e2e round trip is not lossless'
-    e2e_value = px_step_global * args.steps / 1e6 / (e2e_ms / 1e3)
-    e2e_seq_value = px_step_global * args.steps / 1e6 / (e2e_seq_ms / 1e3)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        back, datas = step_e2e(host_sets[s % n_sets])
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms2 = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = px_step_global * args.steps / 1e6 / (float(ms2) / 1e3)
     cont_bytes = sum(len(d) for d in datas)
     img_bytes = n_img * 3 * HW * HW
 
@@ -413,14 +343,10 @@ def run_ours(args):
                        'global_batch': n_global, 'parallelism': 'images sharded over %d GPU(s), no data-path '
                                                                 'collective' % world,
                        'conv_precision': args.precision,
-                       'l2': 'working set >> L2 (1 GB of activations per layer), inputs alternate between batches',
-                       'pipelining': 'none' if args.no_overlap else 'encode of step k+1 overlaps decode of step k '
-                                     '(2 CUDA streams; e2e: 2 host threads); all K round trips inside the timed region'},
+                       'l2': 'working set >> L2 (1 GB of activations per layer), inputs alternate between batches'},
             'bpsp': bpsp, 'bpsp_parity': parity,
             'e2e': {'value': e2e_value, 'unit': 'Mpixels/s', 'h2d_bytes_per_step': img_bytes + cont_bytes,
-                    'd2h_bytes_per_step': cont_bytes + img_bytes, 'sequential_value': e2e_seq_value},
-            'sequential': {'value': value_seq, 'ms_per_step': seq_ms / args.steps,
-                           'note': 'same K round trips without overlapping encode(k+1) and decode(k)'},
+                    'd2h_bytes_per_step': cont_bytes + img_bytes},
             'gpu_launches': None,
             'clocks': clocks,
             'roofline': roofline,
@@ -446,7 +372,6 @@ def main():
                     choices=['fp32', 'tf32', 'tf32x3', 'bf16'])
     ap.add_argument('--images-per-gpu', type=int, default=IMAGES_PER_GPU)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-overlap', action='store_true', help='do not overlap encode(k+1) with decode(k)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
