@@ -36,6 +36,11 @@ __device__ __forceinline__ uint32_t shr_c(uint32_t x, uint32_t n) {   // x >> n,
     asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
     return r;
 }
+__device__ __forceinline__ uint32_t clz_nz(uint32_t x) {             // count leading zeros, x != 0
+    uint32_t r;
+    asm("bfind.shiftamt.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
 struct BitSink {
     uint32_t *out;       // word pointer (big-endian words)
     uint32_t cap_words;
@@ -64,9 +69,112 @@ struct BitSink {
     }
 };
 
+// Emission is kept OFF the coder's serial dependency chain: the coding loop only records, per symbol,
+// the pre-shift `low` and the two shift counts (k decided bits, u underflow shifts) in lane j's
+// registers; every 32 symbols the warp turns the 32 records into bits IN PARALLEL:
+//   pending(j)  = underflow bits owed when symbol j is reached  (segmented sum of u, reset by k > 0)
+//   string(j)   = k(j) > 0 ?  b0, pending(j) x !b0, remaining k-1 bits  :  nothing   (torchac.cpp:186-206)
+//   offset(j)   = exclusive prefix sum of the string lengths
+// one packed warp scan gives all three, the strings are OR-ed into a shared-memory staging area and
+// the completed words are stored coalesced.  Batches containing a run of more than 31 owed bits take
+// the sequential sink instead (rare; same bits).
+constexpr int STAGE_WORDS = 68;      // 31 carried bits + 32 strings of <= 63 bits, + 2 words of slack
+
+struct Emitter {
+    uint32_t *stage;     // shared memory, STAGE_WORDS words, private to the warp
+    BitSink sink;
+    uint32_t pending;    // underflow bits owed (torchac.cpp:165)
+
+    // sequential path: exactly the reference's order of operations
+    __device__ __forceinline__ void emit_serial(uint32_t rec_low, uint32_t k, uint32_t u) {
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t kj = __shfl_sync(FULL, k, j);
+            const uint32_t uj = __shfl_sync(FULL, u, j);
+            const uint32_t lj = __shfl_sync(FULL, rec_low, j);
+            const uint32_t top_bits = shr_c(lj, 32u - kj);
+            if (pending == 0u || kj == 0u) {
+                sink.put(top_bits, (int)kj);
+            } else {
+                const uint32_t b0 = top_bits >> (kj - 1u);
+                sink.put(b0, 1);
+                sink.put_run(b0 ^ 1u, pending);
+                pending = 0u;
+                sink.put(top_bits & ~(1u << (kj - 1u)), (int)kj - 1);
+            }
+            pending += uj;
+        }
+    }
+
+    // one record per lane (k = u = 0 for lanes without a symbol)
+    __device__ __forceinline__ void emit(uint32_t rec_low, uint32_t k, uint32_t u) {
+        const int lane = sink.lane;
+        const uint32_t own = k | (u << 16);
+        uint32_t x = own;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, x, d);
+            if (lane >= d) x += y;
+        }
+        const uint32_t excl = x - own;
+        const uint32_t fmask = __ballot_sync(FULL, k > 0u);
+        const uint32_t below = fmask & ((1u << lane) - 1u);
+        const uint32_t at_last = __shfl_sync(FULL, excl, (31 - __clz((int)below)) & 31);
+        const uint32_t tot = __shfl_sync(FULL, x, 31);
+        const uint32_t at_lastall = __shfl_sync(FULL, excl, (31 - __clz((int)fmask)) & 31);
+        // owed bits when this lane's symbol is reached / bits emitted by the lanes before it
+        const uint32_t pend_before = below ? (excl >> 16) - (at_last >> 16) : pending + (excl >> 16);
+        const uint32_t off = (excl & 0xFFFFu) + (below ? pending + (at_last >> 16) : 0u);
+        const uint32_t total_bits = (tot & 0xFFFFu) + (fmask ? pending + (at_lastall >> 16) : 0u);
+        const uint32_t new_pending = fmask ? (tot >> 16) - (at_lastall >> 16) : pending + (tot >> 16);
+        if (__builtin_expect(__any_sync(FULL, k > 0u && pend_before > 31u), 0)) {
+            emit_serial(rec_low, k, u);
+            return;
+        }
+        const uint32_t nacc = (uint32_t)sink.nacc;
+        stage[lane] = (lane == 0 && nacc) ? (uint32_t)(sink.acc << (32u - nacc)) : 0u;
+        stage[lane + 32] = 0u;
+        if (lane < STAGE_WORDS - 64) stage[lane + 64] = 0u;
+        __syncwarp();
+        if (k > 0u) {
+            const uint32_t T = rec_low >> (32u - k);
+            uint64_t str = T;
+            uint32_t len = k;
+            if (pend_before) {
+                const uint32_t b0 = T >> (k - 1u);
+                const uint32_t rest = T & ~(1u << (k - 1u));
+                const uint32_t run = b0 ? 0u : ((1u << pend_before) - 1u);
+                str = ((((uint64_t)b0 << pend_before) | run) << (k - 1u)) | rest;
+                len = k + pend_before;                                   // <= 63
+            }
+            const uint64_t X = str << (64u - len);                       // left-aligned
+            const uint32_t P = nacc + off;
+            const uint32_t w = P >> 5, b = P & 31u;
+            const uint32_t w0 = (uint32_t)(X >> 32) >> b;
+            const uint32_t w1 = (uint32_t)((X << (32u - b)) >> 32);
+            const uint32_t w2 = b ? (uint32_t)((X << (64u - b)) >> 32) : 0u;
+            if (w0) atomicOr(stage + w, w0);
+            if (w1) atomicOr(stage + w + 1, w1);
+            if (w2) atomicOr(stage + w + 2, w2);
+        }
+        __syncwarp();
+        const uint32_t end = nacc + total_bits;
+        const uint32_t full = end >> 5;                                  // <= 63 completed words
+        for (uint32_t i = lane; i < full; i += 32) {
+            if (sink.wpos + i < sink.cap_words) sink.out[sink.wpos + i] = __byte_perm(stage[i], 0, 0x0123);
+        }
+        const uint32_t partial = stage[full];
+        sink.wpos += full;
+        sink.nacc = (int)(end & 31u);
+        sink.acc = sink.nacc ? (uint64_t)(partial >> (32 - sink.nacc)) : 0ull;
+        pending = new_pending;
+        __syncwarp();
+    }
+};
+
 __global__ void __launch_bounds__(32 * ENC_WARPS_PER_CTA)
 ac_encode_kernel(const l3c_enc_stream_t *__restrict__ streams, int n_streams,
                  uint32_t *__restrict__ out_len) {
+    __shared__ uint32_t s_stage[ENC_WARPS_PER_CTA][STAGE_WORDS];
     const int sid = blockIdx.x * ENC_WARPS_PER_CTA + (threadIdx.x >> 5);
     if (sid >= n_streams) return;
     const int lane = threadIdx.x & 31;
@@ -74,60 +182,69 @@ ac_encode_kernel(const l3c_enc_stream_t *__restrict__ streams, int n_streams,
     const uint32_t *__restrict__ iv = st.intervals;
     const uint32_t n = st.n_sym;
 
-    BitSink sink;
-    sink.out = reinterpret_cast<uint32_t *>(st.out);
-    sink.cap_words = st.out_cap >> 2;
-    sink.wpos = 0;
-    sink.acc = 0;
-    sink.nacc = 0;
-    sink.lane = lane;
+    Emitter em;
+    em.stage = s_stage[threadIdx.x >> 5];
+    em.pending = 0u;
+    em.sink.out = reinterpret_cast<uint32_t *>(st.out);
+    em.sink.cap_words = st.out_cap >> 2;
+    em.sink.wpos = 0;
+    em.sink.acc = 0;
+    em.sink.nacc = 0;
+    em.sink.lane = lane;
 
-    uint32_t low = 0u, high = 0xFFFFFFFFu, pending = 0u;
+    // Coder state is (low, r = high - low): `high` itself is never needed.  Every renormalisation
+    // shift -- "equal MSB" (low <<= 1, high = high << 1 | 1) or "underflow" (the same with the MSBs
+    // forced to 0 / 1) -- maps r to 2r + 1 (mod 2^32) and leaves bit 31 of low clear, so
+    //     r' = (width << s) - 1,   low' = (low << s) & 0x7FFFFFFF      with width = r + 1, s = k + u.
+    uint32_t low = 0u, r = 0xFFFFFFFFu;
+
+    // one coding step (torchac.cpp:171-206); lane j keeps the record of symbol j of the batch
+#define L3C_ENC_STEP(j)                                                                            \
+    {                                                                                              \
+        const uint32_t v = __shfl_sync(FULL, mine, (j));                                           \
+        const uint32_t c_lo = v & 0xFFFFu;                                                         \
+        const uint32_t c_hi = (v >> 16) + 1u;                                                      \
+        /* span * c == r * c + c  (span may be 2^32, keep it out of 32-bit registers) */           \
+        const uint32_t hi16 = (uint32_t)(((uint64_t)r * c_hi + c_hi) >> 16);                       \
+        const uint32_t lo16 = (uint32_t)(((uint64_t)r * c_lo + c_lo) >> 16);                       \
+        const uint32_t width = hi16 - lo16;                /* new high - new low + 1 */            \
+        low += lo16;                                                                               \
+        const uint32_t high = low + width - 1u;                                                    \
+        /* renormalisation: k "equal MSB" shifts, then u "underflow" shifts */                     \
+        const uint32_t k = (uint32_t)__clz((int)(low ^ high));                                     \
+        const uint32_t u = clz_nz(~shl_c(shl_c(low & ~high, k), 1u));                              \
+        if (lane == (j)) {                                                                         \
+            rec_low = low;                                                                         \
+            rec_ku = k | (u << 8);                                                                 \
+        }                                                                                          \
+        low = shl_c(shl_c(low, k), u) & 0x7FFFFFFFu;                                               \
+        r = shl_c(shl_c(width, k), u) - 1u;                                                        \
+    }
 
     uint32_t next = (lane < n) ? __ldg(iv + lane) : 0u;
     for (uint32_t base = 0; base < n; base += 32) {
         const uint32_t mine = next;
         const uint32_t nb = base + 32 + lane;
         next = (nb < n) ? __ldg(iv + nb) : 0u;              // prefetch the next 32 intervals
-        const int cnt = (n - base < 32u) ? (int)(n - base) : 32;
-#pragma unroll 4
-        for (int j = 0; j < cnt; ++j) {
-            const uint32_t v = __shfl_sync(FULL, mine, j);
-            const uint32_t c_lo = v & 0xFFFFu;
-            const uint32_t c_hi = (v >> 16) + 1u;
-            const uint32_t r = high - low;                   // span - 1
-            // span * c  ==  r * c + c   (span may be 2^32, keep it out of 32-bit registers)
-            const uint64_t p_hi = (uint64_t)r * c_hi + c_hi;
-            const uint64_t p_lo = (uint64_t)r * c_lo + c_lo;
-            high = low - 1u + (uint32_t)(p_hi >> 16);
-            low = low + (uint32_t)(p_lo >> 16);
-
-            // renormalisation: k "equal MSB" shifts, then u "underflow" shifts, done as one shift by s
-            const uint32_t k = (uint32_t)__clz((int)(low ^ high));
-            const uint32_t u = (uint32_t)__clz((int)~shl_c(shl_c(low & ~high, k), 1u));
-            const uint32_t s = k + u;
-            const uint32_t msb = u ? 0x80000000u : 0u;
-            const uint32_t top_bits = shr_c(low, 32u - k);               // the k decided bits (k = 0 -> 0)
-            if (__builtin_expect(pending == 0u || k == 0u, 1)) {
-                sink.put(top_bits, (int)k);                              // put(x, 0) is a no-op
-            } else {
-                const uint32_t b0 = top_bits >> (k - 1u);
-                sink.put(b0, 1);
-                sink.put_run(b0 ^ 1u, pending);
-                pending = 0u;
-                sink.put(top_bits & ~(1u << (k - 1u)), (int)k - 1);
-            }
-            pending += u;
-            low = shl_c(low, s) & ~msb;
-            high = shl_c(high, s) | ~shl_c(0xFFFFFFFFu, s) | msb;
+        uint32_t rec_low = 0u, rec_ku = 0u;
+        if (n - base >= 32u) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) L3C_ENC_STEP(j)
+        } else {
+            const int cnt = (int)(n - base);
+#pragma unroll 1
+            for (int j = 0; j < cnt; ++j) L3C_ENC_STEP(j)
         }
+        em.emit(rec_low, rec_ku & 0xFFu, rec_ku >> 8);
     }
+#undef L3C_ENC_STEP
 
-    // termination (torchac.cpp:209-219): one more bit + the owed underflow bits, zero-padded
-    pending += 1u;
+    // termination (torchac.cpp:209-219): one more bit + the owed underflow bits, zero-padded --
+    // i.e. a one-bit record met with pending + 1 owed bits
     const uint32_t fin = (low < 0x40000000u) ? 0u : 1u;
-    sink.put(fin, 1);
-    sink.put_run(fin ^ 1u, pending);
+    em.pending += 1u;
+    em.emit(lane == 0 ? (fin << 31) : 0u, lane == 0 ? 1u : 0u, 0u);
+    BitSink &sink = em.sink;
     const uint32_t total = sink.wpos * 4u + (uint32_t)((sink.nacc + 7) >> 3);
     if (sink.nacc > 0) {
         const uint32_t w = (uint32_t)(sink.acc << (32 - sink.nacc));
@@ -195,8 +312,52 @@ __device__ __noinline__ uint32_t foreign_count16(uint32_t value, uint32_t low, u
     return (uint32_t)(((off * 65536ull - 1ull) / ((uint64_t)r + 1ull)) & 0xFFFFull);
 }
 
+// Decoder state: (low, r = high - low, dv = value - low).  Every renormalisation shift maps
+// r -> 2r + 1 and dv -> 2dv + next code bit (mod 2^32) and leaves bit 31 of low clear -- for the
+// "equal MSB" and the "underflow" shifts alike -- so neither `high`, `value` nor the reference's MSB
+// fix-ups (torchac.cpp:345-364) are needed on the serial chain.  Saved/restored as (low, high, value).
 struct CoderState {
-    uint32_t low, high, value;
+    uint32_t low, r, dv;
+    __device__ __forceinline__ void reset(uint32_t value) {
+        low = 0u;
+        r = 0xFFFFFFFFu;
+        dv = value;
+    }
+    __device__ __forceinline__ void restore(const uint32_t *st) {
+        low = st[0];
+        r = st[1] - st[0];
+        dv = st[2] - st[0];
+    }
+    __device__ __forceinline__ void save(uint32_t *st) const {
+        st[0] = low;
+        st[1] = low + r;
+        st[2] = low + dv;
+    }
+    // narrow to [c_lo, c_hi) / 2^16 of the current interval, renormalise, refill  (torchac.cpp:339-364)
+    template <class Source>
+    __device__ __forceinline__ void update(uint32_t c_lo, uint32_t c_hi, Source &src) {
+        const uint32_t hi16 = (uint32_t)(((uint64_t)r * c_hi + c_hi) >> 16);
+        const uint32_t lo16 = (uint32_t)(((uint64_t)r * c_lo + c_lo) >> 16);
+        const uint32_t width = hi16 - lo16;                 // new high - new low + 1
+        const uint32_t lo = low + lo16;
+        const uint32_t hi = lo + width - 1u;
+        const uint32_t d = dv - lo16;
+        const uint32_t k = (uint32_t)__clz((int)(lo ^ hi));
+        const uint32_t u = clz_nz(~shl_c(shl_c(lo & ~hi, k), 1u));
+        const uint32_t s = k + u;
+        if (__builtin_expect(s <= 32u, 1)) {
+            const uint32_t bits = src.take(s);
+            low = shl_c(lo, s) & 0x7FFFFFFFu;
+            r = shl_c(width, s) - 1u;
+            dv = shl_c(d, s) | bits;
+        } else {
+            const uint32_t bk = src.take(k);
+            const uint32_t bu = src.take(u);
+            low = shl_c(shl_c(lo, k), u) & 0x7FFFFFFFu;
+            r = shl_c(shl_c(width, k), u) - 1u;
+            dv = shl_c(shl_c(d, k) | bk, u) | bu;
+        }
+    }
 };
 
 // CDF row held by a warp.  EPL = 8: lane l holds entries 8l..8l+7 (two per register) plus the first
@@ -262,42 +423,19 @@ __device__ __forceinline__ int search_row(const RowRegs<1> &row, uint32_t r, uin
 template <int EPL, bool FULLROW>
 __device__ __forceinline__ int decode_step(const RowRegs<EPL> &cur, CoderState &cs, BitSource &src, int lane, int L,
                                            bool update) {
-    uint32_t r = cs.high - cs.low;                              // span - 1
-    const uint32_t dv = cs.value - cs.low;
+    const uint32_t r = cs.r;                                    // span - 1
+    const uint32_t dv = cs.dv;
     uint64_t target = ((uint64_t)dv + 1ull) << 16;
     uint32_t r_cmp = r;
     if (__builtin_expect(dv > r, 0)) {
         // value outside [low, high] (corrupt / foreign input): use the reference's truncated count;
         // cdf[m] <= count  <=>  cdf[m] * 1 < count + 1
-        target = (uint64_t)foreign_count16(cs.value, cs.low, r) + 1ull;
+        target = (uint64_t)foreign_count16(cs.low + dv, cs.low, r) + 1ull;
         r_cmp = 0u;
     }
     uint32_t c_lo, c_hi;
     const int sym = search_row<FULLROW>(cur, r_cmp, target, lane, L, c_lo, c_hi);
-    if (update) {
-        const uint64_t p_hi = (uint64_t)r * c_hi + c_hi;
-        const uint64_t p_lo = (uint64_t)r * c_lo + c_lo;
-        const uint32_t high = cs.low - 1u + (uint32_t)(p_hi >> 16);
-        const uint32_t low = cs.low + (uint32_t)(p_lo >> 16);
-        // renormalisation: k "equal MSB" shifts, then u "underflow" shifts (see file header)
-        const uint32_t k = (uint32_t)__clz((int)(low ^ high));
-        const uint32_t y = low & ~high;
-        const uint32_t u = (uint32_t)__clz((int)~shl_c(shl_c(y, k), 1u));
-        const uint32_t s = k + u;
-        const uint32_t msb = u ? 0x80000000u : 0u;
-        if (__builtin_expect(s <= 32u, 1)) {
-            const uint32_t bits = src.take(s);
-            cs.low = shl_c(low, s) & ~msb;
-            cs.high = shl_c(high, s) | ~shl_c(0xFFFFFFFFu, s) | msb;
-            cs.value = (shl_c(cs.value, s) | bits) ^ msb;
-        } else {
-            const uint32_t bk = src.take(k);
-            const uint32_t bu = src.take(u);
-            cs.low = shl_c(shl_c(low, k), u) & ~msb;
-            cs.high = shl_c(shl_c(high, k) | ~shl_c(0xFFFFFFFFu, k), u) | ~shl_c(0xFFFFFFFFu, u) | msb;
-            cs.value = (shl_c(shl_c(cs.value, k) | bk, u) | bu) ^ msb;
-        }
-    }
+    if (update) cs.update(c_lo, c_hi, src);
     return sym;
 }
 
@@ -319,14 +457,10 @@ ac_decode_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, in
 
     CoderState cs;
     if (first == 0) {
-        cs.low = 0u;
-        cs.high = 0xFFFFFFFFu;
         src.seek(bit0);
-        cs.value = src.take(32);
+        cs.reset(src.take(32));
     } else {
-        cs.low = st.state[0];
-        cs.high = st.state[1];
-        cs.value = st.state[2];
+        cs.restore(st.state);
         src.seek(st.state[3] + bit0);
     }
 
@@ -375,9 +509,7 @@ ac_decode_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, in
     }
 
     if (lane == 0 && st.state != nullptr) {
-        st.state[0] = cs.low;
-        st.state[1] = cs.high;
-        st.state[2] = cs.value;
+        cs.save(st.state);
         st.state[3] = src.pos - bit0;
     }
 }
@@ -552,14 +684,10 @@ ac_decode256_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams,
     const uint32_t bit0 = src.open(st.in, st.in_len);
     CoderState cs;
     if (first == 0) {
-        cs.low = 0u;
-        cs.high = 0xFFFFFFFFu;
         src.seek(bit0);
-        cs.value = src.take(32);
+        cs.reset(src.take(32));
     } else {
-        cs.low = st.state[0];
-        cs.high = st.state[1];
-        cs.value = st.state[2];
+        cs.restore(st.state);
         src.seek(st.state[3] + bit0);
     }
     for (uint32_t gi = 0; gi < n_groups; ++gi) {
@@ -572,14 +700,14 @@ ac_decode256_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams,
             if (i < last) {
                 const uint4 a = ring[g * G + d][0][lane];
                 const uint4 b = ring[g * G + d][1][lane];
-                const uint32_t r = cs.high - cs.low;
-                const uint32_t dv = cs.value - cs.low;
+                const uint32_t r = cs.r;
+                const uint32_t dv = cs.dv;
                 // cdf[m] <= count  <=>  cdf[m] * span < (value - low + 1) << 16   (no division; the
                 // float-estimated count was measured ~85 cycles longer on the dependent chain)
                 uint64_t target = ((uint64_t)dv + 1ull) << 16;
                 uint32_t r_cmp = r;
                 if (__builtin_expect(dv > r, 0)) {                            // corrupt / foreign input only
-                    target = (uint64_t)foreign_count16(cs.value, cs.low, r) + 1ull;
+                    target = (uint64_t)foreign_count16(cs.low + dv, cs.low, r) + 1ull;
                     r_cmp = 0u;
                 }
                 // rows are sorted: the last proposal whose cdf[m] passes is the numerically largest
@@ -602,40 +730,15 @@ ac_decode256_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams,
                 const uint32_t best = max(max(m01, m23), max(m45, m67));
                 const uint32_t top = __reduce_max_sync(FULL, best);
                 if (lane == 0) tops[g * G + d] = top;
-                if (i != n - 1) {                                             // torchac.cpp:335-337
-                    const uint32_t c_lo = top >> 16;
-                    const uint32_t c_hi = (top & 0xFFFFu) + 1u;
-                    const uint64_t p_hi = (uint64_t)r * c_hi + c_hi;
-                    const uint64_t p_lo = (uint64_t)r * c_lo + c_lo;
-                    const uint32_t high = cs.low - 1u + (uint32_t)(p_hi >> 16);
-                    const uint32_t low = cs.low + (uint32_t)(p_lo >> 16);
-                    const uint32_t k = (uint32_t)__clz((int)(low ^ high));
-                    const uint32_t y = low & ~high;
-                    const uint32_t u = (uint32_t)__clz((int)~shl_c(shl_c(y, k), 1u));
-                    const uint32_t s = k + u;
-                    const uint32_t msb = u ? 0x80000000u : 0u;
-                    if (__builtin_expect(s <= 32u, 1)) {
-                        const uint32_t bits = src.take(s);
-                        cs.low = shl_c(low, s) & ~msb;
-                        cs.high = shl_c(high, s) | ~shl_c(0xFFFFFFFFu, s) | msb;
-                        cs.value = (shl_c(cs.value, s) | bits) ^ msb;
-                    } else {
-                        const uint32_t bk = src.take(k);
-                        const uint32_t bu = src.take(u);
-                        cs.low = shl_c(shl_c(low, k), u) & ~msb;
-                        cs.high = shl_c(shl_c(high, k) | ~shl_c(0xFFFFFFFFu, k), u) | ~shl_c(0xFFFFFFFFu, u) | msb;
-                        cs.value = (shl_c(shl_c(cs.value, k) | bk, u) | bu) ^ msb;
-                    }
-                }
+                if (i != n - 1)                                               // torchac.cpp:335-337
+                    cs.update(top >> 16, (top & 0xFFFFu) + 1u, src);
             }
         }
         __syncwarp();
         mbar_arrive(bar0 + 16 + 8 * g);                                       // empty[g]
     }
     if (lane == 0 && st.state != nullptr) {
-        st.state[0] = cs.low;
-        st.state[1] = cs.high;
-        st.state[2] = cs.value;
+        cs.save(st.state);
         st.state[3] = src.pos - bit0;
     }
 }

@@ -61,6 +61,35 @@ def test_encode_decode_cdf_bit_exact(L, n_sym):
         assert (torchac.decode_cdf(_as_t(cdf), b'').numpy() == ac.decode(cdf, b'')).all()
 
 
+def _underflow_case(rng, n_sym, L=3):
+    """Symbols whose interval straddles the midpoint: `u` underflow shifts and no decided bit per
+    symbol, so the owed ("pending") bits pile up over many symbols -- well past 31, across the
+    encoder's 32-symbol batches -- until an off-centre symbol releases them (torchac.cpp:196-206)."""
+    half = 32768
+    rows = np.zeros((n_sym, L + 1), np.int64)
+    for i in range(n_sym):
+        w = int(rng.integers(1, 200))
+        rows[i, :L] = [0, half - w, half + int(rng.integers(1, 200))]
+    sym = np.ones(n_sym, np.int16)                       # the straddling symbol ...
+    for i in rng.integers(0, n_sym, size=max(1, n_sym // 37)):
+        sym[i] = int(rng.integers(0, 3))                 # ... with a few releases sprinkled in
+    return rows.astype(np.uint16), sym
+
+
+@pytest.mark.parametrize('n_sym', [5, 31, 32, 33, 64, 1000, 4099])
+def test_long_underflow_runs_bit_exact(n_sym):
+    from l3c_pytorch_b200 import torchac
+    rng = np.random.default_rng(n_sym)
+    for trial in range(3):
+        cdf, sym = _underflow_case(rng, n_sym)
+        if trial == 2:
+            sym[:] = 1                                   # never released before the terminator
+        want = ac.encode(cdf, sym)
+        got = torchac.encode_cdf(_as_t(cdf), torch.from_numpy(sym))
+        assert got == want
+        assert (torchac.decode_cdf(_as_t(cdf), want).numpy() == sym).all()
+
+
 def test_dropin_errors():
     from l3c_pytorch_b200 import torchac
     cdf = _as_t(_random_table(np.random.default_rng(0), 4, 25, False))
