@@ -298,6 +298,19 @@ struct BitSource {
             nextw = word(wbase + 2);
         }
     }
+    // same as skip(), written so that it compiles to predicated straight-line code (fast decode loop)
+    __device__ __forceinline__ void skip_flat(uint32_t n) {
+        pos += n;
+        const bool cross = (pos >> 5) != wbase;
+        const uint32_t idx = wbase + 3u;
+        const int rem = (int)end_byte - (int)(4u * idx);
+        uint32_t w = 0u;
+        if (cross && rem > 0) w = __byte_perm(__ldg(base + idx), 0, 0x0123);
+        if (rem < 4) w &= 0xFFFFFFFFu << ((32 - 8 * rem) & 31);            // rem <= 0: w is 0 already
+        win = cross ? ((win << 32) | (uint64_t)nextw) : win;
+        nextw = cross ? w : nextw;
+        wbase += cross ? 1u : 0u;
+    }
     __device__ __forceinline__ uint32_t take(uint32_t n) { // n <= 32; take(0) == 0
         const uint32_t v = shr_c(peek32(), 32u - n);
         skip(n);
@@ -332,6 +345,27 @@ struct CoderState {
         st[0] = low;
         st[1] = low + r;
         st[2] = low + dv;
+    }
+    // update() for the speculative fast loop: no branches; returns true when the step needed more
+    // than 32 shifts (then the new state is garbage and the caller replays the group with update())
+    template <class Source>
+    __device__ __forceinline__ bool update_flat(uint32_t c_lo, uint32_t c_hi, Source &src) {
+        const uint32_t peek = src.peek32();
+        const uint32_t hi16 = (uint32_t)(((uint64_t)r * c_hi + c_hi) >> 16);
+        const uint32_t lo16 = (uint32_t)(((uint64_t)r * c_lo + c_lo) >> 16);
+        const uint32_t width = hi16 - lo16;
+        const uint32_t lo = low + lo16;
+        const uint32_t hi = lo + width - 1u;
+        const uint32_t d = dv - lo16;
+        const uint32_t k = (uint32_t)__clz((int)(lo ^ hi));
+        const uint32_t u = clz_nz(~shl_c(shl_c(lo & ~hi, k), 1u));
+        const uint32_t s = k + u;
+        low = shl_c(shl_c(lo, k), u) & 0x7FFFFFFFu;
+        r = shl_c(shl_c(width, k), u) - 1u;
+        // (d << s) | (next s code bits): two clamped funnel shifts, the first one overlaps the clz of u
+        dv = __funnelshift_lc(shl_c(peek, k), __funnelshift_lc(peek, d, k), u);
+        src.skip_flat(s);
+        return s > 32u;
     }
     // narrow to [c_lo, c_hi) / 2^16 of the current interval, renormalise, refill  (torchac.cpp:339-364)
     template <class Source>
@@ -506,6 +540,117 @@ ac_decode_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, in
             const int sym = decode_step<EPL, FULLROW>(ring[d], cs, src, lane, L, i < upd_end);
             if (lane == 0) sym_out[i] = (uint8_t)sym;
         }
+    }
+
+    if (lane == 0 && st.state != nullptr) {
+        cs.save(st.state);
+        st.state[3] = src.pos - bit0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// decoder, alphabets of at most 32 symbols (bottleneck and uniform-prior streams): one CDF entry per
+// lane, ballot + popc + two shuffles.  Groups of 8 symbols run as straight-line speculative code
+// (see v3::ac_decode256_kernel); a group that trips the sticky flag is replayed with decode_step().
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * DEC_WARPS_PER_CTA)
+ac_decode32_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, int L,
+                   uint32_t first, uint32_t count) {
+    constexpr int D = 8;   // symbols per group = row prefetch distance
+    const int sid = blockIdx.x * DEC_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (sid >= n_streams) return;
+    const int lane = threadIdx.x & 31;
+    const l3c_dec_stream_t st = streams[sid];
+    const uint32_t n = st.n_sym;
+    if (first >= n) return;
+    const uint32_t last = (count > n - first) ? n : first + count;   // exclusive
+
+    BitSource src;
+    const uint32_t bit0 = src.open(st.in, st.in_len);
+    CoderState cs;
+    if (first == 0) {
+        src.seek(bit0);
+        cs.reset(src.take(32));
+    } else {
+        cs.restore(st.state);
+        src.seek(st.state[3] + bit0);
+    }
+
+    const uint16_t *__restrict__ table = st.table;
+    const int64_t pitch = st.row_pitch;
+    uint8_t *__restrict__ sym_out = st.sym_out;
+    const bool vec_out = ((reinterpret_cast<uintptr_t>(sym_out) | first) & 3u) == 0u;
+    const bool in_row = lane < L;
+
+    const uint32_t upd_end = (last == n) ? n - 1 : last;          // symbols < upd_end update the state
+    const uint32_t main_end = first + ((upd_end - first) / D) * D;
+
+    uint32_t ring[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const uint32_t i = first + d;
+        ring[d] = (i < main_end) ? (uint32_t)__ldg(table + (int64_t)i * pitch + lane) : 0u;
+    }
+    uint32_t base = first;
+    bool exact = false;        // sticky: once a group had to be replayed the stream is corrupt anyway
+    for (; base < main_end; base += D) {
+        if (!exact) {
+            const CoderState cs0 = cs;
+            const BitSource src0 = src;
+            bool bad = false;
+            uint32_t packed[D / 4];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const uint32_t i = base + d;
+                const uint32_t v = ring[d];
+                if (i + D < main_end) ring[d] = (uint32_t)__ldg(table + (int64_t)(i + D) * pitch + lane);
+                const uint32_t r = cs.r, dv = cs.dv;
+                bad |= dv > r;
+                // cdf[m] <= count  <=>  mulhi(cdf[m] << 16, span) <= dv
+                const uint32_t e = v << 16;
+                const bool f = (lane == 0) || (in_row && (uint32_t)(((uint64_t)e * r + e) >> 32) <= dv);
+                const int nt = __popc(__ballot_sync(FULL, f));
+                const uint32_t c_lo = __shfl_sync(FULL, v, nt - 1);
+                const uint32_t nxt = __shfl_sync(FULL, v, nt & 31);
+                const uint32_t c_hi = (nt >= L) ? 0x10000u : nxt;
+                bad |= cs.update_flat(c_lo, c_hi, src);
+                if ((d & 3) == 0) packed[d >> 2] = 0u;
+                packed[d >> 2] |= (uint32_t)(nt - 1) << (8 * (d & 3));
+            }
+            if (__builtin_expect(!bad, 1)) {
+                if (lane == 0) {
+                    if (vec_out) {
+#pragma unroll
+                        for (int q = 0; q < D / 4; ++q)
+                            *reinterpret_cast<uint32_t *>(sym_out + base + 4 * q) = packed[q];
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < D; ++d) sym_out[base + d] = (uint8_t)(packed[d >> 2] >> (8 * (d & 3)));
+                    }
+                }
+                continue;
+            }
+            cs = cs0;
+            src = src0;
+            exact = true;
+        }
+#pragma unroll 1
+        for (int d = 0; d < D; ++d) {
+            const uint32_t i = base + d;
+            RowRegs<1> cur;
+            cur.load(table + (int64_t)i * pitch, lane);
+            const int sym = decode_step<1, false>(cur, cs, src, lane, L, true);
+            if (lane == 0) sym_out[i] = (uint8_t)sym;
+        }
+    }
+    // tail (< D symbols, may contain the stream's final symbol, which leaves the state untouched:
+    // torchac.cpp:335-337)
+#pragma unroll 1
+    for (uint32_t i = base; i < last; ++i) {
+        RowRegs<1> cur;
+        cur.load(table + (int64_t)i * pitch, lane);
+        const int sym = decode_step<1, false>(cur, cs, src, lane, L, i < upd_end);
+        if (lane == 0) sym_out[i] = (uint8_t)sym;
     }
 
     if (lane == 0 && st.state != nullptr) {
@@ -690,44 +835,75 @@ ac_decode256_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams,
         cs.restore(st.state);
         src.seek(st.state[3] + bit0);
     }
+    const uint32_t upd_end = (last == n) ? n - 1u : last;                     // symbols < upd_end update the state
     for (uint32_t gi = 0; gi < n_groups; ++gi) {
         const uint32_t g = gi & 1u;
         mbar_wait(bar0 + 8 * g, (gi >> 1) & 1u);                              // full[g]
         const uint32_t ibase = first + gi * G;
+        bool replay = ibase + G > upd_end;                                    // ragged / final group
+        if (!replay) {
+            // Speculative fast path: straight-line code, no per-symbol checks.  The two things that
+            // cannot happen on a valid stream -- code value outside [low, high], more than 32
+            // renormalisation shifts -- only set a sticky flag; the group is then replayed exactly.
+            const CoderState cs0 = cs;
+            const BitSource src0 = src;
+            bool bad = false;
+            const uint4 *slot = &ring[g * G][0][lane];
+            uint4 a = slot[0], b = slot[32];
+#pragma unroll 1
+            for (int d = 0; d < G; ++d) {
+                const uint4 *nslot = slot + ((d + 1) & (G - 1)) * 64;         // next symbol's proposals
+                const uint4 na = nslot[0], nb = nslot[32];
+                const uint32_t r = cs.r, dv = cs.dv;
+                bad |= dv > r;
+                // cdf[m] <= count  <=>  cdf[m] * span < (dv + 1) << 16  <=>  mulhi(cdf[m] << 16, span) <= dv
+                const uint32_t pk[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                bool f[8];
 #pragma unroll
-        for (int d = 0; d < G; ++d) {
-            const uint32_t i = ibase + d;
-            if (i < last) {
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t e = pk[j] & 0xFFFF0000u;
+                    f[j] = (uint32_t)(((uint64_t)e * r + e) >> 32) <= dv;
+                }
+                f[0] = f[0] || (lane == 0);                                   // symbol 0 is the floor
+                // rows are sorted: the last passing proposal is the numerically largest
+                const uint32_t m01 = f[1] ? pk[1] : (f[0] ? pk[0] : 0u);
+                const uint32_t m23 = f[3] ? pk[3] : (f[2] ? pk[2] : 0u);
+                const uint32_t m45 = f[5] ? pk[5] : (f[4] ? pk[4] : 0u);
+                const uint32_t m67 = f[7] ? pk[7] : (f[6] ? pk[6] : 0u);
+                const uint32_t top = __reduce_max_sync(FULL, max(max(m01, m23), max(m45, m67)));
+                if (lane == 0) tops[g * G + d] = top;
+                bad |= cs.update_flat(top >> 16, (top & 0xFFFFu) + 1u, src);
+                a = na;
+                b = nb;
+            }
+            if (__builtin_expect(bad, 0)) {
+                cs = cs0;
+                src = src0;
+                replay = true;
+            }
+        }
+        if (replay) {
+#pragma unroll 1
+            for (int d = 0; d < G; ++d) {
+                const uint32_t i = ibase + d;
+                if (i >= last) break;
                 const uint4 a = ring[g * G + d][0][lane];
                 const uint4 b = ring[g * G + d][1][lane];
                 const uint32_t r = cs.r;
                 const uint32_t dv = cs.dv;
-                // cdf[m] <= count  <=>  cdf[m] * span < (value - low + 1) << 16   (no division; the
-                // float-estimated count was measured ~85 cycles longer on the dependent chain)
                 uint64_t target = ((uint64_t)dv + 1ull) << 16;
                 uint32_t r_cmp = r;
-                if (__builtin_expect(dv > r, 0)) {                            // corrupt / foreign input only
+                if (dv > r) {                                                 // corrupt / foreign input only
                     target = (uint64_t)foreign_count16(cs.low + dv, cs.low, r) + 1ull;
                     r_cmp = 0u;
                 }
-                // rows are sorted: the last proposal whose cdf[m] passes is the numerically largest
                 const uint32_t pk[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                uint32_t m01, m23, m45, m67;
-                {
-                    const bool f0 = (lane == 0) || below(pk[0] >> 16, r_cmp, target);   // symbol 0 is the floor
-                    const bool f1 = below(pk[1] >> 16, r_cmp, target);
-                    const bool f2 = below(pk[2] >> 16, r_cmp, target);
-                    const bool f3 = below(pk[3] >> 16, r_cmp, target);
-                    const bool f4 = below(pk[4] >> 16, r_cmp, target);
-                    const bool f5 = below(pk[5] >> 16, r_cmp, target);
-                    const bool f6 = below(pk[6] >> 16, r_cmp, target);
-                    const bool f7 = below(pk[7] >> 16, r_cmp, target);
-                    m01 = f1 ? pk[1] : (f0 ? pk[0] : 0u);
-                    m23 = f3 ? pk[3] : (f2 ? pk[2] : 0u);
-                    m45 = f5 ? pk[5] : (f4 ? pk[4] : 0u);
-                    m67 = f7 ? pk[7] : (f6 ? pk[6] : 0u);
+                uint32_t best = 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool fj = ((lane | j) == 0) || below(pk[j] >> 16, r_cmp, target);
+                    best = fj ? max(best, pk[j]) : best;
                 }
-                const uint32_t best = max(max(m01, m23), max(m45, m67));
                 const uint32_t top = __reduce_max_sync(FULL, best);
                 if (lane == 0) tops[g * G + d] = top;
                 if (i != n - 1)                                               // torchac.cpp:335-337
@@ -797,7 +973,7 @@ extern "C" int l3c_ac_decode_streams(const l3c_dec_stream_t *streams_dev, int n_
     const dim3 blk(32 * DEC_WARPS_PER_CTA);
     cudaStream_t st = (cudaStream_t)stream;
     if (L <= 32) {
-        ac_decode_kernel<1, false><<<grid, blk, 0, st>>>(streams_dev, n_streams, L, first, count);
+        ac_decode32_kernel<<<grid, blk, 0, st>>>(streams_dev, n_streams, L, first, count);
     } else if (L == 256) {
         v3::ac_decode256_kernel<<<n_streams, 64, 0, st>>>(streams_dev, n_streams, first, count);
     } else {
