@@ -37,6 +37,7 @@ extern "C" {
 #define L3C_ECUDA (-2)    /* CUDA runtime error                                                          */
 #define L3C_EOVERFLOW (-3)/* output buffer too small                                                     */
 #define L3C_ENODEV (-4)   /* no sm_100 device                                                            */
+#define L3C_EUNSUPPORTED (-5) /* optional facility not offered by this driver (caller may do without)      */
 
 const char *l3c_last_error(void);
 int l3c_version(void);
@@ -215,6 +216,22 @@ int l3c_symbols_to_values(const uint8_t *sym_dev, const float *values_dev, const
 /* Pillow-compatible bicubic x0.5 on uint8 planes [N][3][H][W] -> [N][3][H/2][W/2]
  * (dataloaders/images_loader.py:277-293 via PIL.Image.resize(BICUBIC); RGB baselines only). */
 int l3c_bicubic_half_u8(const uint8_t *in_dev, int N, int H, int W, uint8_t *out_dev, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * E. Execution resources
+ * ---------------------------------------------------------------------------------------- */
+
+/* Streams confined to two disjoint groups of SMs of the current device (driver green contexts):
+ * `n_a` streams (high priority) whose kernels only run on a group of about `sm_a` SMs (the driver
+ * rounds up to its granularity, 8 on sm_90+), `n_b` streams on the remaining SMs.  Used by the
+ * pipelined RGB decode (reference: the strictly serial R -> G -> B loop of bitcoding.py:199-237) so
+ * that the latency-bound decoder warps do not share SMs with the CDF-row builders.  The streams
+ * belong to the primary context (same memory, events interoperate) and live until process exit;
+ * repeated calls with the same `sm_a` return the same streams.  *sm_a_out / *sm_b_out (optional)
+ * receive the actual group sizes.  L3C_EUNSUPPORTED if the driver cannot partition: the caller then
+ * uses ordinary streams (slower, same results). */
+int l3c_partition_streams(int sm_a, int n_a, void **streams_a, int n_b, void **streams_b,
+                          int *sm_a_out, int *sm_b_out);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,7 @@ CONV_RELU = 1
 CONV_PIXEL_SHUFFLE2 = 2
 CONV_ROUND_TF32 = 4
 PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_BF16 = 0, 1, 2, 3
+E_UNSUPPORTED = -5          # L3C_EUNSUPPORTED
 PRECISIONS = {'fp32': PREC_FP32, 'tf32': PREC_TF32, 'tf32x3': PREC_TF32X3, 'bf16': PREC_BF16}
 
 # numpy dtypes of the stream descriptor structs (l3c_enc_stream_t / l3c_dec_stream_t)
@@ -60,22 +61,32 @@ _SIGNATURES = {
     'l3c_symbols_to_values': (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_void_p]),
     'l3c_bicubic_half_u8': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'l3c_pack_streams': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    'l3c_partition_streams': (c_int, [c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 EXPORTS = sorted(_SIGNATURES)
 
 
-def _load():
-    if not os.path.isfile(SO_PATH):
-        # in-tree build (nvcc cross-compiles without a GPU); raises if nvcc is missing
-        from . import build as _build
-        _build.build()
-    lib = ctypes.CDLL(SO_PATH)
+def _bind(path):
+    lib = ctypes.CDLL(path)
     for name, (restype, argtypes) in _SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.restype = restype
         fn.argtypes = argtypes
     return lib
+
+
+def _load():
+    from . import build as _build
+    if not os.path.isfile(SO_PATH):
+        # in-tree build (nvcc cross-compiles without a GPU); raises if nvcc is missing
+        _build.build()
+    try:
+        return _bind(SO_PATH)
+    except AttributeError:
+        # a library left over from an older source tree: rebuild once, then fail loudly
+        _build.build(force=True)
+        return _bind(SO_PATH)
 
 
 lib = _load()

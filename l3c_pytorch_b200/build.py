@@ -12,7 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(HERE, 'libl3c_b200.so')
-SOURCES = ['capi.cu', 'range_coder.cu', 'dmll.cu', 'conv_ffma.cu', 'conv_tcgen05.cu', 'bicubic.cu']
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+SOURCES = ['capi.cu', 'range_coder.cu', 'dmll.cu', 'conv_ffma.cu', 'conv_tcgen05.cu', 'bicubic.cu', 'partition.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--fmad=true',
               '-DL3C_BUILDING_DSO']
@@ -27,7 +28,7 @@ def _newest_source_mtime():
 def build(verbose=False, force=False):
     if not force and os.path.isfile(SO) and os.path.getmtime(SO) >= _newest_source_mtime():
         return SO
-    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    nvcc = NVCC
     objs = []
     build_dir = os.path.join(HERE, 'build')
     os.makedirs(build_dir, exist_ok=True)

@@ -12,6 +12,7 @@ for a whole batch of equally sized images with
     stream | 4-byte magic).
 Decoding uploads the concatenated containers once and decodes every stream in place.
 """
+import os
 import struct
 
 import numpy as np
@@ -245,9 +246,7 @@ class BatchCodec(object):
         d['state'][:] = state.data_ptr() + 16 * (np.arange(N)[:, None] * C + np.arange(C)[None, :])
         descs = [E._desc_to_device(np.ascontiguousarray(d[:, c]), dev) for c in range(C)]
         cur = torch.cuda.current_stream()
-        if not hasattr(self, '_streams'):
-            self._streams = [[torch.cuda.Stream(device=dev) for _ in range(3)] for _ in range(2)]
-        s_bld, s_dec = self._streams
+        s_bld, s_dec = self._rgb_streams(dev, N * C)
         start = torch.cuda.Event()
         start.record(cur)
         for st in s_bld[:C] + s_dec[:C]:
@@ -278,6 +277,26 @@ class BatchCodec(object):
             e.record(st)
             cur.wait_event(e)
         del prev_dec
+
+    def _rgb_streams(self, dev, n_decoders):
+        """(row-builder streams, decoder streams), three each.  The decoder streams own a group of SMs
+        (one SM per decoder CTA up to half the GPU; l3c_partition_streams) and the row builders get
+        the rest: a latency-bound decoder warp that shares its SM with row-builder warps runs ~1.5x
+        slower.  L3C_SM_PARTITION=0, or a driver without green contexts, gives ordinary streams."""
+        key = (str(dev), n_decoders)
+        cache = self.__dict__.setdefault('_rgb_stream_cache', {})
+        if key not in cache:
+            part = None
+            if os.environ.get('L3C_SM_PARTITION', '1') != '0':
+                n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+                want = min(max(8, -(-n_decoders // 8) * 8), (n_sm // 16) * 8)
+                part = E.partition_streams(dev, want, 3, 3)
+            if part is not None:
+                cache[key] = (part[1], part[0])
+            else:
+                cache[key] = ([torch.cuda.Stream(device=dev) for _ in range(3)],
+                              [torch.cuda.Stream(device=dev) for _ in range(3)])
+        return cache[key]
 
     def decode_device(self, blob, offs, lens, shapes):
         """Decode streams that already sit in HBM: `blob` uint8 device buffer (readable 4 bytes past

@@ -265,16 +265,21 @@ struct BitSource {
     uint32_t end_byte;     // mis + in_len: first byte (relative to base) that is past the stream
     uint32_t wbase;        // word index of the upper half of `win`
     uint64_t win;          // words wbase, wbase+1
-    uint32_t nextw;        // word wbase+2, prefetched
+    uint32_t nextw;        // word wbase+2, ready to use
+    uint32_t raw;          // word wbase+3 as loaded (little-endian, unmasked): consumed one refill
+                           // later, so its load latency never lands on the coder's serial chain
     uint32_t pos;          // next unread bit, relative to base; invariant 0 <= pos - 32*wbase < 32
 
-    __device__ __forceinline__ uint32_t word(uint32_t i) const {
+    __device__ __forceinline__ uint32_t load_raw(uint32_t i) const {
+        return ((int)end_byte - (int)(4u * i) > 0) ? __ldg(base + i) : 0u;
+    }
+    __device__ __forceinline__ uint32_t finish(uint32_t w_raw, uint32_t i) const {   // big-endian, zero past the end
         const int rem = (int)end_byte - (int)(4u * i);
-        if (rem <= 0) return 0u;
-        uint32_t w = __byte_perm(__ldg(base + i), 0, 0x0123);
-        if (rem < 4) w &= 0xFFFFFFFFu << (8 * (4 - rem));
+        uint32_t w = __byte_perm(w_raw, 0, 0x0123);
+        if (rem < 4) w = (rem <= 0) ? 0u : (w & (0xFFFFFFFFu << (8 * (4 - rem))));
         return w;
     }
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return finish(load_raw(i), i); }
     __device__ __forceinline__ uint32_t open(const uint8_t *in, uint32_t len) {
         const uintptr_t a = reinterpret_cast<uintptr_t>(in);
         const uint32_t mis = (uint32_t)(a & 3u);
@@ -286,6 +291,7 @@ struct BitSource {
         wbase = p >> 5;
         win = ((uint64_t)word(wbase) << 32) | (uint64_t)word(wbase + 1);
         nextw = word(wbase + 2);
+        raw = load_raw(wbase + 3);
         pos = p;
     }
     // the next 32 bits (not consumed)
@@ -295,20 +301,27 @@ struct BitSource {
         if ((pos >> 5) != wbase) {
             win = (win << 32) | (uint64_t)nextw;
             wbase++;
-            nextw = word(wbase + 2);
+            nextw = finish(raw, wbase + 2);
+            raw = load_raw(wbase + 3);
         }
     }
-    // same as skip(), written so that it compiles to predicated straight-line code (fast decode loop)
+    // same as skip(), written so that it compiles to predicated straight-line code (fast decode loops)
     __device__ __forceinline__ void skip_flat(uint32_t n) {
         pos += n;
         const bool cross = (pos >> 5) != wbase;
-        const uint32_t idx = wbase + 3u;
-        const int rem = (int)end_byte - (int)(4u * idx);
-        uint32_t w = 0u;
-        if (cross && rem > 0) w = __byte_perm(__ldg(base + idx), 0, 0x0123);
-        if (rem < 4) w &= 0xFFFFFFFFu << ((32 - 8 * rem) & 31);            // rem <= 0: w is 0 already
+        const uint32_t fin = finish(raw, wbase + 3);       // becomes word (wbase+1)+2
+        const uint32_t idx = wbase + 4u;
+        const bool fetch = cross & ((int)end_byte - (int)(4u * idx) > 0);
         win = cross ? ((win << 32) | (uint64_t)nextw) : win;
-        nextw = cross ? w : nextw;
+        nextw = cross ? fin : nextw;
+        // predicated load straight into `raw` (no select behind it: a select would wait for the load).
+        // When nothing is fetched the stale value is harmless: finish() zeroes words past the end.
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.u32 p, %2, 0;\n\t"
+            "@p ld.global.nc.u32 %0, [%1];\n\t}"
+            : "+r"(raw)
+            : "l"(base + idx), "r"((uint32_t)fetch));
         wbase += cross ? 1u : 0u;
     }
     __device__ __forceinline__ uint32_t take(uint32_t n) { // n <= 32; take(0) == 0
@@ -585,35 +598,51 @@ ac_decode32_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, 
     const uint32_t upd_end = (last == n) ? n - 1 : last;          // symbols < upd_end update the state
     const uint32_t main_end = first + ((upd_end - first) / D) * D;
 
-    uint32_t ring[D];
+    // lane l keeps entry l as the packed proposal (cdf[l] << 16) | (cdf[l+1] - 1) (2^16 after the last
+    // entry), built when the row arrives: rows are sorted, so the warp-max over the passing proposals
+    // is the decoded symbol's and carries both interval bounds -- one REDUX instead of
+    // ballot -> popc -> two shuffles on the serial chain (the symbol index itself is off the chain).
+    // (the packing is done when a row is used, not when it is loaded: a shuffle right behind the load
+    // would put the HBM latency of every row on the critical path)
+    auto pack_row = [&](uint32_t v) -> uint32_t {
+        uint32_t nx = __shfl_down_sync(FULL, v, 1);
+        if (lane + 1 >= L) nx = 0x10000u;
+        return in_row ? ((v << 16) | ((nx - 1u) & 0xFFFFu)) : 0u;
+    };
+    // rows are fetched two groups ahead: a group's rows are packed at its start, so they must have been
+    // requested at least a whole group (~1.5 us) earlier for HBM latency to stay hidden
+    uint32_t ring[D], ahead[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const uint32_t i = first + d;
         ring[d] = (i < main_end) ? (uint32_t)__ldg(table + (int64_t)i * pitch + lane) : 0u;
+        ahead[d] = (i + D < main_end) ? (uint32_t)__ldg(table + (int64_t)(i + D) * pitch + lane) : 0u;
     }
     uint32_t base = first;
-    bool exact = false;        // sticky: once a group had to be replayed the stream is corrupt anyway
     for (; base < main_end; base += D) {
-        if (!exact) {
+        {
             const CoderState cs0 = cs;
             const BitSource src0 = src;
             bool bad = false;
             uint32_t packed[D / 4];
+            uint32_t prop[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) prop[d] = pack_row(ring[d]);   // off the serial chain
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 const uint32_t i = base + d;
-                const uint32_t v = ring[d];
-                if (i + D < main_end) ring[d] = (uint32_t)__ldg(table + (int64_t)(i + D) * pitch + lane);
+                const uint32_t pk = prop[d];
+                ring[d] = ahead[d];
+                // (clamped, not predicated: a conditional load into the array costs a select that waits for it)
+                ahead[d] = (uint32_t)__ldg(table + (int64_t)min(i + 2 * D, main_end - 1u) * pitch + lane);
                 const uint32_t r = cs.r, dv = cs.dv;
-                bad |= dv > r;
+                const uint32_t span = r + 1u;                        // 2^32 wraps to 0: replay (stream start)
+                bad |= (dv > r) || (span == 0u);
                 // cdf[m] <= count  <=>  mulhi(cdf[m] << 16, span) <= dv
-                const uint32_t e = v << 16;
-                const bool f = (lane == 0) || (in_row && (uint32_t)(((uint64_t)e * r + e) >> 32) <= dv);
-                const int nt = __popc(__ballot_sync(FULL, f));
-                const uint32_t c_lo = __shfl_sync(FULL, v, nt - 1);
-                const uint32_t nxt = __shfl_sync(FULL, v, nt & 31);
-                const uint32_t c_hi = (nt >= L) ? 0x10000u : nxt;
-                bad |= cs.update_flat(c_lo, c_hi, src);
+                const bool f = (lane == 0) || (in_row && __umulhi(pk & 0xFFFF0000u, span) <= dv);
+                const uint32_t top = __reduce_max_sync(FULL, f ? pk : 0u);
+                const int nt = __popc(__ballot_sync(FULL, f));       // symbol + 1 (not on the chain)
+                bad |= cs.update_flat(top >> 16, (top & 0xFFFFu) + 1u, src);
                 if ((d & 3) == 0) packed[d >> 2] = 0u;
                 packed[d >> 2] |= (uint32_t)(nt - 1) << (8 * (d & 3));
             }
@@ -630,9 +659,8 @@ ac_decode32_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, 
                 }
                 continue;
             }
-            cs = cs0;
+            cs = cs0;                 // replay this group exactly (the ring already holds the next group's rows)
             src = src0;
-            exact = true;
         }
 #pragma unroll 1
         for (int d = 0; d < D; ++d) {
@@ -855,15 +883,13 @@ ac_decode256_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams,
                 const uint4 *nslot = slot + ((d + 1) & (G - 1)) * 64;         // next symbol's proposals
                 const uint4 na = nslot[0], nb = nslot[32];
                 const uint32_t r = cs.r, dv = cs.dv;
-                bad |= dv > r;
+                const uint32_t span = r + 1u;                                 // 2^32 wraps to 0: replay (stream start)
+                bad |= (dv > r) || (span == 0u);
                 // cdf[m] <= count  <=>  cdf[m] * span < (dv + 1) << 16  <=>  mulhi(cdf[m] << 16, span) <= dv
                 const uint32_t pk[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                 bool f[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t e = pk[j] & 0xFFFF0000u;
-                    f[j] = (uint32_t)(((uint64_t)e * r + e) >> 32) <= dv;
-                }
+                for (int j = 0; j < 8; ++j) f[j] = __umulhi(pk[j] & 0xFFFF0000u, span) <= dv;
                 f[0] = f[0] || (lane == 0);                                   // symbol 0 is the floor
                 // rows are sorted: the last passing proposal is the numerically largest
                 const uint32_t m01 = f[1] ? pk[1] : (f[0] ? pk[0] : 0u);

@@ -34,6 +34,31 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+_PARTITIONS = {}
+
+
+def partition_streams(device, sm_a, n_a, n_b):
+    """Streams confined to two disjoint SM groups of `device` (l3c_partition_streams):
+    -> (streams_a, streams_b, sm_a, sm_b) as torch ExternalStreams, or None when the driver cannot
+    partition (the caller then uses ordinary streams).  Cached per (device, sm_a)."""
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), sm_a, n_a, n_b)
+    if key not in _PARTITIONS:
+        a = (ctypes.c_void_p * n_a)()
+        b = (ctypes.c_void_p * n_b)()
+        got_a, got_b = ctypes.c_int(0), ctypes.c_int(0)
+        with torch.cuda.device(key[0]):
+            rc = lib.l3c_partition_streams(sm_a, n_a, a, n_b, b, ctypes.byref(got_a), ctypes.byref(got_b))
+        if rc == _lib.E_UNSUPPORTED:
+            _PARTITIONS[key] = None
+        else:
+            check(rc)
+            _PARTITIONS[key] = ([torch.cuda.ExternalStream(int(p), device=key[0]) for p in a],
+                                [torch.cuda.ExternalStream(int(p), device=key[0]) for p in b],
+                                got_a.value, got_b.value)
+    return _PARTITIONS[key]
+
+
 def require_cuda(t, name):
     if not t.is_cuda:
         raise ValueError('%s must be a CUDA tensor (l3c_pytorch_b200 has no CPU path)' % name)

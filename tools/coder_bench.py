@@ -57,6 +57,9 @@ def run(L, n_streams, n_sym, peaked, rare=False, own_tables=False):
                           enc_ns_per_sym=t_enc * 1e6 / n_sym, dec_ns_per_sym=t_dec * 1e6 / n_sym, ok=ok)))
 
 if __name__ == '__main__':
-    for (L, ns, n, pk, rare, own) in [(256, 48, 65536, True, False, False), (256, 48, 65536, True, True, False),
-                                      (25, 80, 65536, True, True, False)]:
-        run(L, ns, n, pk, rare, own)
+    only = int(sys.argv[sys.argv.index('--only') + 1]) if '--only' in sys.argv else None
+    for ci, (L, ns, n, pk, rare, own) in enumerate([(256, 48, 65536, True, False, False), (256, 48, 65536, True, True, False),
+                                      (25, 80, 65536, True, True, False), (256, 48, 65536, True, True, True),
+                                      (25, 80, 65536, True, True, True)]):
+        if only is None or only == ci:
+            run(L, ns, n, pk, rare, own)

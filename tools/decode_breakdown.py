@@ -32,7 +32,7 @@ for it in range(3):
     mark('end'); torch.cuda.synchronize()
 t0 = marks[0][1]
 print(json.dumps({n: round(t0.elapsed_time(e), 2) for n, e in marks}))
-for nch in ((64,) if '--quick' in sys.argv else (8, 16, 32, 64)):
+for nch in ((64,) if '--quick' in sys.argv else (32, 64, 96, 128)):
     codec._decode_rgb_pipelined = lambda *a, **k: orig_rgb(*a, n_chunks=nch, **k)
     best = 1e9
     for it in range(2):
