@@ -191,10 +191,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def shapes_of(info):
+        return [(C, H, W) for (_, C, H, W) in info['shapes']]
+
     def step_resident(imgs):
         blob, info = codec.encode_batch(imgs, to_host=False)
-        shapes = [(C, H, W) for (_, C, H, W) in info['shapes']]
-        S = codec.decode_device(blob, info['stream_offsets'], info['lens'], shapes)
+        S = codec.decode_device(blob, info['stream_offsets'], info['lens'], shapes_of(info))
         return S, info
 
     def step_e2e(host_imgs):
@@ -203,10 +205,60 @@ def run_ours(args):
         back = torch.cat(dec, 0).to(torch.uint8).cpu()        # D2H of the result
         return back, datas
 
+    # Software pipelining over steps (the default): the decode of a batch is bound by the serial range
+    # decoder and leaves most SMs idle, so the encode of the NEXT batch runs beside it, on a stream that
+    # is confined to the SMs the decoders do not own.  K complete round trips -- including the
+    # un-overlapped first encode and last decode -- lie inside the timed region.
+    main_stream = torch.cuda.current_stream()
+    side_stream = codec.encode_stream(dev, 3 * n_img)
+
+    def run_resident(steps, first_set=0):
+        if not args.pipeline:
+            for s in range(steps):
+                S, info = step_resident(dev_sets[(first_set + s) % n_sets])
+            return S, info
+        dbg = os.environ.get('L3C_BENCH_DEBUG')
+        with torch.cuda.stream(side_stream):
+            job = codec.encode_begin(dev_sets[first_set % n_sets])
+        for s in range(steps):
+            t0 = time.perf_counter()
+            blob, info = job.finish(to_host=False)
+            t1 = time.perf_counter()
+            job = None
+            if s + 1 < steps:
+                with torch.cuda.stream(side_stream):
+                    job = codec.encode_begin(dev_sets[(first_set + s + 1) % n_sets])
+            t2 = time.perf_counter()
+            main_stream.wait_event(info['ready'])
+            blob.record_stream(main_stream)
+            S = codec.decode_device(blob, info['stream_offsets'], info['lens'], shapes_of(info))
+            if dbg:
+                print('pipelined step %d: finish %.1f ms, begin(next) %.1f ms, decode issue %.1f ms'
+                      % (s, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (time.perf_counter() - t2)), file=sys.stderr)
+        return S, info
+
+    def run_e2e(steps, first_set=0):
+        if not args.pipeline:
+            for s in range(steps):
+                back, datas = step_e2e(host_sets[(first_set + s) % n_sets])
+            return back, datas
+        job = bc.encode_batch_begin(host_sets[first_set % n_sets], stream=side_stream)
+        for s in range(steps):
+            datas, _ = job.finish()
+            job = None
+            if s + 1 < steps:
+                job = bc.encode_batch_begin(host_sets[(first_set + s + 1) % n_sets], stream=side_stream)
+            dec = bc.decode_batch(datas)
+            back = torch.cat(dec, 0).to(torch.uint8).cpu()    # D2H of the result
+        return back, datas
+
     # ---- warm-up + correctness (outside the timed region)
     for w in range(max(args.warmup, 1)):
         S, info = step_resident(dev_sets[w % n_sets])
     assert torch.equal(S, dev_sets[(max(args.warmup, 1) - 1) % n_sets]), 'round trip is not lossless'
+    if args.pipeline:                      # the side stream has its own allocator pool: warm it up too
+        S, info = run_resident(max(args.warmup, 2))
+        assert torch.equal(S, dev_sets[(max(args.warmup, 2) - 1) % n_sets]), 'pipelined round trip is not lossless'
     sizes = info['sizes']
     counts = l3c_dist.gather_byte_counts(sizes, n_global, rank, world)       # the one collective (NCCL)
     bpsp = l3c_dist.global_bpsp(counts, 3 * HW * HW)
@@ -231,8 +283,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     launches0 = E.LAUNCHES['n']
-    for s in range(args.steps):
-        S, info = step_resident(dev_sets[s % n_sets])
+    S, info = run_resident(args.steps)
     launches_timed = E.LAUNCHES['n'] - launches0
     e1.record()
     barrier()
@@ -244,16 +295,38 @@ def run_ours(args):
     ms_total = float(ms)
     px_step_global = n_global * HW * HW
     value = px_step_global * args.steps / 1e6 / (ms_total / 1e3)
+    assert torch.equal(S, dev_sets[(args.steps - 1) % n_sets]), 'timed round trip is not lossless'
+
+    def timed_sequential(fn):
+        """the same K steps strictly one after the other (reported beside the pipelined numbers)"""
+        barrier()
+        tw = time.perf_counter()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for s in range(args.steps):
+            fn(s % n_sets)
+        b.record()
+        barrier()
+        t = torch.tensor([max(a.elapsed_time(b), 0.0), (time.perf_counter() - tw) * 1e3], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    seq_value = seq_e2e = None
+    if args.pipeline:
+        seq_ms, _ = timed_sequential(lambda i: step_resident(dev_sets[i]))
+        seq_value = px_step_global * args.steps / 1e6 / (seq_ms / 1e3)
 
     # ---- timed: end to end through the public API (host buffers, copies inside)
     back, datas = step_e2e(host_sets[0])
     assert torch.equal(back, host_sets[0]), 'e2e round trip is not lossless'
+    if args.pipeline:
+        run_e2e(2)
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for s in range(args.steps):
-        back, datas = step_e2e(host_sets[s % n_sets])
+    back, datas = run_e2e(args.steps)
     e1.record()
     barrier()
     wall = time.perf_counter() - t0
@@ -261,6 +334,10 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = px_step_global * args.steps / 1e6 / (float(ms2) / 1e3)
+    assert torch.equal(back, host_sets[(args.steps - 1) % n_sets]), 'timed e2e round trip is not lossless'
+    if args.pipeline:
+        seq_ev, seq_wall = timed_sequential(lambda i: step_e2e(host_sets[i]))
+        seq_e2e = px_step_global * args.steps / 1e6 / (max(seq_ev, seq_wall) / 1e3)
     cont_bytes = sum(len(d) for d in datas)
     img_bytes = n_img * 3 * HW * HW
 
@@ -343,10 +420,15 @@ def run_ours(args):
                        'global_batch': n_global, 'parallelism': 'images sharded over %d GPU(s), no data-path '
                                                                 'collective' % world,
                        'conv_precision': args.precision,
+                       'pipelining': ('encode of batch k+1 overlaps decode of batch k (separate SM partitions); all '
+                                      '%d round trips, incl. the un-overlapped first encode and last decode, are '
+                                      'inside the timed region; "sequential" = the same steps one after the other'
+                                      % args.steps) if args.pipeline else 'none (sequential steps)',
                        'l2': 'working set >> L2 (1 GB of activations per layer), inputs alternate between batches'},
             'bpsp': bpsp, 'bpsp_parity': parity,
             'e2e': {'value': e2e_value, 'unit': 'Mpixels/s', 'h2d_bytes_per_step': img_bytes + cont_bytes,
-                    'd2h_bytes_per_step': cont_bytes + img_bytes},
+                    'd2h_bytes_per_step': cont_bytes + img_bytes, 'sequential_value': seq_e2e},
+            'sequential': {'value': seq_value, 'unit': 'Mpixels/s'},
             'gpu_launches': None,
             'clocks': clocks,
             'roofline': roofline,
@@ -372,6 +454,8 @@ def main():
                     choices=['fp32', 'tf32', 'tf32x3', 'bf16'])
     ap.add_argument('--images-per-gpu', type=int, default=IMAGES_PER_GPU)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-pipeline', dest='pipeline', action='store_false',
+                    help='strictly sequential steps: encode(k), decode(k), encode(k+1), ...')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

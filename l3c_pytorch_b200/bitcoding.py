@@ -110,14 +110,27 @@ class Bitcoding(object):
     # B200-first batch API
     def encode_batch(self, imgs_u8):
         """imgs_u8: uint8 [N,3,H,W] (any device) -> (list of container bytes, bpsp list)."""
+        return self.encode_batch_begin(imgs_u8).finish()
+
+    def encode_batch_begin(self, imgs_u8, stream=None):
+        """Asynchronous encode_batch: enqueues the upload and the whole GPU side on `stream` (default:
+        the current stream) and returns a job at once; job.finish() -> (containers, bpsps).  With
+        `stream=self.side_stream(N)` the encode runs beside a decode_batch of another batch: the
+        decode is bound by the serial range decoder and leaves most of the GPU idle."""
         factor = 2 ** self.blueprint.net.config_ms.num_scales
         pt = pad.padding_tuple(imgs_u8.shape[-2], imgs_u8.shape[-1], factor)
-        x = imgs_u8.to(self._device(), non_blocking=True)
-        if any(pt):
-            x = torch.nn.functional.pad(x, pt, 'constant')
-        datas, _ = self.codec.encode_batch(x.contiguous(), pt)
-        nsub = int(np.prod(x.shape[1:]))
-        return datas, [len(d) * 8 / nsub for d in datas]
+        stream = stream if stream is not None else torch.cuda.current_stream(self._device())
+        with torch.cuda.stream(stream):
+            x = imgs_u8.to(self._device(), non_blocking=True)
+            if any(pt):
+                x = torch.nn.functional.pad(x, pt, 'constant')
+            x = x.contiguous()
+            job = self.codec.encode_begin(x, pt)
+        return _BatchEncodeJob(job, int(np.prod(x.shape[1:])))
+
+    def side_stream(self, n_images):
+        """Stream for encode_batch_begin() calls that should overlap a decode_batch of `n_images`."""
+        return self.codec.encode_stream(self._device(), 3 * n_images)
 
     def decode_batch(self, datas):
         """list of container bytes (any mix of shapes) -> list of int64 1CHW tensors (GPU)."""
@@ -135,6 +148,15 @@ class Bitcoding(object):
                     img = pad.undo_pad(img, *pt)
                 outs[i] = img
         return outs
+
+
+class _BatchEncodeJob:
+    def __init__(self, job, nsub):
+        self.job, self.nsub = job, nsub
+
+    def finish(self):
+        datas, _ = self.job.finish(to_host=True)
+        return datas, [len(d) * 8 / self.nsub for d in datas]
 
 
 # --- header field helpers (bitcoding.py:326-375), little-endian -------------------------------

@@ -88,6 +88,53 @@ def parse_container(data):
     return pad_tuple, scales
 
 
+class EncodeJob:
+    """An encode in flight (BatchCodec.encode_begin).  finish() waits for the stream lengths, lays the
+    containers out, gathers the streams into one blob on the job's stream and (to_host) brings the
+    bytes back: same results as encode_batch."""
+
+    def finish(self, to_host=True):
+        codec, N, per_img, caps, shapes = self.codec, self.N, self.per_img, self.caps, self.shapes
+        self.coded.synchronize()                                                   # sync #1 (tiny)
+        lens = self.lens_host.numpy().astype(np.int64).reshape(N, per_img)
+        if (lens > caps[None, :]).any():
+            raise RuntimeError('range coder output exceeded its slot (corrupt CDF?)')
+        with torch.cuda.stream(self.stream):
+            # ---- container layout + gather + single D2H
+            layout = ContainerLayout(shapes)
+            sizes, pieces_all, dst = [], [], np.zeros((N, per_img), np.int64)
+            pos = 0
+            starts = []
+            for n in range(N):
+                total, pieces, offs = layout.header_and_offsets(lens[n], self.pad_tuple)
+                starts.append(pos)
+                dst[n] = pos + np.asarray(offs, np.int64)
+                pieces_all.append(pieces)
+                sizes.append(total)
+                pos += (total + 15) & ~15
+            blob = torch.empty(pos + 16, dtype=torch.uint8, device=self.dev)
+            E.pack_streams(self.desc_dev, self.lens_dev, dst.reshape(-1), N * per_img, blob)
+            info = dict(sizes=sizes, starts=starts, lens=lens, shapes=shapes, out=self.out, stream_offsets=dst)
+            if not to_host:
+                self.packed = torch.cuda.Event()
+                self.packed.record(self.stream)
+                info['ready'] = self.packed          # consumers on another stream wait for this event
+                self.keep = None
+                return blob, info
+            host = torch.empty(blob.shape, dtype=torch.uint8, pin_memory=True)
+            host.copy_(blob, non_blocking=True)
+            self.stream.synchronize()                                              # sync #2
+        self.keep = None
+        buf = host.numpy()
+        datas = []
+        for n in range(N):
+            s0 = starts[n]
+            for (o, b) in pieces_all[n]:
+                buf[s0 + o:s0 + o + len(b)] = np.frombuffer(b, np.uint8)
+            datas.append(buf[s0:s0 + sizes[n]].tobytes())
+        return datas, info
+
+
 class BatchCodec(object):
     def __init__(self, blueprint):
         self.blueprint = blueprint
@@ -128,6 +175,13 @@ class BatchCodec(object):
         """imgs_u8: uint8 [N,3,H,W] on the GPU, H and W multiples of 2**num_scales.
         Returns a list of N container byte strings (or, with to_host=False, the device blob,
         per-image sizes and offsets, leaving the bytes in HBM).  `out`: a precomputed network Out."""
+        return self.encode_begin(imgs_u8, pad_tuple, out).finish(to_host)
+
+    def encode_begin(self, imgs_u8, pad_tuple=(0, 0, 0, 0), out=None):
+        """First half of encode_batch: enqueues the whole GPU side of an encode (networks, intervals,
+        the range-coder launch, the copy of the stream lengths to pinned memory) on the CURRENT stream
+        and returns without waiting.  EncodeJob.finish() completes it.  Lets a caller overlap the
+        encode of one batch with other work, e.g. the latency-bound decode of the previous batch."""
         assert imgs_u8.dtype == torch.uint8 and imgs_u8.dim() == 4 and imgs_u8.shape[1] == 3
         dev = imgs_u8.device
         N = imgs_u8.shape[0]
@@ -166,38 +220,16 @@ class BatchCodec(object):
                 d['out'][:, j] = slots.data_ptr() + np.arange(N, dtype=np.int64) * img_slot_bytes + slot_off[j]
                 j += 1
         desc_dev, lens_dev = E.ac_encode_streams(desc, dev)
-        lens = lens_dev.cpu().numpy().astype(np.int64).reshape(N, per_img)       # sync #1 (tiny)
-        if (lens > caps[None, :]).any():
-            raise RuntimeError('range coder output exceeded its slot (corrupt CDF?)')
-
-        # ---- container layout + gather + single D2H
-        layout = ContainerLayout(shapes)
-        sizes, pieces_all, dst = [], [], np.zeros((N, per_img), np.int64)
-        pos = 0
-        starts = []
-        for n in range(N):
-            total, pieces, offs = layout.header_and_offsets(lens[n], pad_tuple)
-            starts.append(pos)
-            dst[n] = pos + np.asarray(offs, np.int64)
-            pieces_all.append(pieces)
-            sizes.append(total)
-            pos += (total + 15) & ~15
-        blob = torch.empty(pos + 16, dtype=torch.uint8, device=dev)
-        E.pack_streams(desc_dev, lens_dev, dst.reshape(-1), N * per_img, blob)
-        info = dict(sizes=sizes, starts=starts, lens=lens, shapes=shapes, out=out, stream_offsets=dst)
-        if not to_host:
-            return blob, info
-        host = torch.empty(blob.shape, dtype=torch.uint8, pin_memory=True)
-        host.copy_(blob, non_blocking=True)
-        torch.cuda.current_stream().synchronize()                                 # sync #2
-        buf = host.numpy()
-        datas = []
-        for n in range(N):
-            s0 = starts[n]
-            for (o, b) in pieces_all[n]:
-                buf[s0 + o:s0 + o + len(b)] = np.frombuffer(b, np.uint8)
-            datas.append(buf[s0:s0 + sizes[n]].tobytes())
-        return datas, info
+        lens_host = torch.empty(lens_dev.shape, dtype=lens_dev.dtype, pin_memory=True)
+        lens_host.copy_(lens_dev, non_blocking=True)
+        job = EncodeJob()
+        job.codec, job.stream = self, torch.cuda.current_stream()
+        job.coded = torch.cuda.Event()
+        job.coded.record(job.stream)
+        job.keep = (imgs_u8, ivs, slots)                       # alive until finish()
+        job.N, job.per_img, job.caps, job.shapes, job.out = N, per_img, caps, shapes, out
+        job.pad_tuple, job.desc_dev, job.lens_dev, job.lens_host, job.dev = pad_tuple, desc_dev, lens_dev, lens_host, dev
+        return job
 
     # ------------------------------------------------------------------------------------------
     def decode_batch(self, datas, to_host=True):
@@ -278,25 +310,33 @@ class BatchCodec(object):
             cur.wait_event(e)
         del prev_dec
 
+    def encode_stream(self, dev, n_decoders):
+        """A stream for encodes that run beside a decode (EncodeJob pipelining): confined to the SM group
+        of the row builders, so that its persistent conv kernels never sit on the decoders' SMs."""
+        self._rgb_streams(dev, n_decoders)
+        return self._rgb_stream_cache[(str(dev), n_decoders)][2]
+
     def _rgb_streams(self, dev, n_decoders):
         """(row-builder streams, decoder streams), three each.  The decoder streams own a group of SMs
-        (one SM per decoder CTA up to half the GPU; l3c_partition_streams) and the row builders get
-        the rest: a latency-bound decoder warp that shares its SM with row-builder warps runs ~1.5x
-        slower.  L3C_SM_PARTITION=0, or a driver without green contexts, gives ordinary streams."""
+        (one SM per two decoder CTAs, up to half the GPU; l3c_partition_streams) and the row builders
+        get the rest: a latency-bound decoder warp that shares its SM with row-builder warps runs
+        ~1.5x slower.  L3C_SM_PARTITION=0, or a driver without green contexts, gives ordinary streams."""
         key = (str(dev), n_decoders)
         cache = self.__dict__.setdefault('_rgb_stream_cache', {})
         if key not in cache:
             part = None
             if os.environ.get('L3C_SM_PARTITION', '1') != '0':
                 n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-                want = min(max(8, -(-n_decoders // 8) * 8), (n_sm // 16) * 8)
-                part = E.partition_streams(dev, want, 3, 3)
+                # two decoder CTAs per SM (measured at 16 x 512^2: 48 / 24 / 16 SMs -> decode 95 / 86 / 93 ms)
+                want = min(max(8, -(-n_decoders // 16) * 8), (n_sm // 16) * 8)
+                want = int(os.environ.get('L3C_DEC_SMS', want))           # bring-up knob
+                part = E.partition_streams(dev, want, 3, 4)
             if part is not None:
-                cache[key] = (part[1], part[0])
+                cache[key] = (part[1][:3], part[0], part[1][3])
             else:
                 cache[key] = ([torch.cuda.Stream(device=dev) for _ in range(3)],
-                              [torch.cuda.Stream(device=dev) for _ in range(3)])
-        return cache[key]
+                              [torch.cuda.Stream(device=dev) for _ in range(3)], torch.cuda.Stream(device=dev))
+        return cache[key][:2]
 
     def decode_device(self, blob, offs, lens, shapes):
         """Decode streams that already sit in HBM: `blob` uint8 device buffer (readable 4 bytes past

@@ -18,6 +18,18 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+int sm_count() {
+    static int counts[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!counts[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        counts[dev] = n;
+    }
+    return counts[dev];
+}
+
 int conv2d_ffma(const l3c_conv_t &p, cudaStream_t st);
 int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st);
 

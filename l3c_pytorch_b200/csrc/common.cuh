@@ -38,6 +38,9 @@ void set_error(const char *fmt, ...);
         }                                                                                \
     } while (0)
 
+int sm_count();                          // SMs of the current device
+int stream_sm_count(cudaStream_t st);    // SMs available to kernels launched into `st` (partition.cu)
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -703,12 +703,9 @@ int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st) {
     q.cout_rows = p.cout_pad;
     q.total_tiles = p.N * q.tiles_x * q.tiles_y * cout_tiles;
 
-    static int n_sm = 0;
     static bool configured = false;
+    const int n_sm = stream_sm_count(st);          // the stream may be confined to a group of SMs
     if (!configured) {
-        int dev = 0;
-        L3C_CUDA(cudaGetDevice(&dev));
-        L3C_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         L3C_CUDA(cudaFuncSetAttribute(conv3x3_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         L3C_CUDA(cudaFuncSetAttribute(conv3x3_tcgen05_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       227 * 1024));

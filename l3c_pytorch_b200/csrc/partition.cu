@@ -65,6 +65,22 @@ __global__ void partition_probe_kernel(int *out) {
 }
 
 }  // namespace
+
+// SMs a kernel launched into `st` can use: the group size for a partition stream handed out by
+// l3c_partition_streams, the whole device otherwise (persistent kernels size their grid with it)
+int stream_sm_count(cudaStream_t st) {
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        for (const Partition *p : g_parts) {
+            for (CUstream s : p->streams_a)
+                if ((cudaStream_t)s == st) return p->sm_a;
+            for (CUstream s : p->streams_b)
+                if ((cudaStream_t)s == st) return p->sm_b;
+        }
+    }
+    return sm_count();
+}
+
 }  // namespace l3c
 
 extern "C" int l3c_partition_streams(int sm_a, int n_a, void **streams_a, int n_b, void **streams_b,

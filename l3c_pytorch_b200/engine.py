@@ -336,9 +336,15 @@ def dmll_channel_params(l, x_dec, C, K, rgb, c):
 # ----------------------------------------------------------------------------------------------
 # range coder
 # ----------------------------------------------------------------------------------------------
+def _to_device_async(arr, device):
+    """numpy -> device through pinned staging, asynchronous on the current stream.  (A copy from pageable
+    memory first waits for everything already queued on the stream: the host would stall behind the
+    GPU at every descriptor upload and could never run ahead to feed a second stream.)"""
+    return torch.from_numpy(np.ascontiguousarray(arr)).pin_memory().to(device, non_blocking=True)
+
+
 def _desc_to_device(arr, device):
-    t = torch.from_numpy(arr.view(np.uint8).reshape(-1))
-    return t.to(device, non_blocking=False)
+    return _to_device_async(arr.view(np.uint8).reshape(-1), device)
 
 
 def ac_encode_streams(desc_np, device):
@@ -352,7 +358,7 @@ def ac_encode_streams(desc_np, device):
 
 
 def pack_streams(desc_dev, lens_dev, dst_off_np, n, blob):
-    off = torch.from_numpy(dst_off_np.astype(np.int64)).to(blob.device)
+    off = _to_device_async(dst_off_np.astype(np.int64), blob.device)
     check(lib.l3c_pack_streams(_ptr(desc_dev), _ptr(lens_dev), _ptr(off), n, _ptr(blob), _stream_ptr()))
     LAUNCHES['n'] += 1
 
