@@ -223,7 +223,8 @@ int l3c_bicubic_half_u8(const uint8_t *in_dev, int N, int H, int W, uint8_t *out
 
 /* Streams confined to two disjoint groups of SMs of the current device (driver green contexts):
  * `n_a` streams (high priority) whose kernels only run on a group of about `sm_a` SMs (the driver
- * rounds up to its granularity, 8 on sm_90+), `n_b` streams on the remaining SMs.  Used by the
+ * rounds up to its granularity, 8 on sm_90+), `n_b` streams on the remaining SMs (the first three of
+ * them high priority, further ones default priority).  Used by the
  * pipelined RGB decode (reference: the strictly serial R -> G -> B loop of bitcoding.py:199-237) so
  * that the latency-bound decoder warps do not share SMs with the CDF-row builders.  The streams
  * belong to the primary context (same memory, events interoperate) and live until process exit;

@@ -128,9 +128,12 @@ extern "C" int l3c_partition_streams(int sm_a, int n_a, void **streams_a, int n_
         g_parts.push_back(p);
         part = p;
     }
-    auto grow = [&](std::vector<CUstream> &v, CUgreenCtx ctx, int n, int priority) -> bool {
+    // group B: the first three streams (CDF-row builders of a decode) outrank any further ones (used
+    // for work that merely runs beside a decode, e.g. the encode of the next batch)
+    auto grow = [&](std::vector<CUstream> &v, CUgreenCtx ctx, int n, int n_high) -> bool {
         while ((int)v.size() < n) {
             CUstream s = nullptr;
+            const int priority = ((int)v.size() < n_high) ? -1 : 0;
             if (drv.GreenCtxStreamCreate(&s, ctx, CU_STREAM_NON_BLOCKING, priority) != CUDA_SUCCESS) return false;
             // the runtime must accept the stream: one empty launch, checked
             partition_probe_kernel<<<1, 32, 0, (cudaStream_t)s>>>(nullptr);
@@ -139,7 +142,7 @@ extern "C" int l3c_partition_streams(int sm_a, int n_a, void **streams_a, int n_
         }
         return true;
     };
-    if (!grow(part->streams_a, part->ctx_a, n_a, -1) || !grow(part->streams_b, part->ctx_b, n_b, 0)) {
+    if (!grow(part->streams_a, part->ctx_a, n_a, 64) || !grow(part->streams_b, part->ctx_b, n_b, 3)) {
         set_error("l3c_partition_streams: could not create / use a partition stream on device %d", dev);
         return L3C_EUNSUPPORTED;
     }
