@@ -300,3 +300,57 @@ def test_rgb_shared_batch32_round_trip():
         assert abs(np.mean(bpsps) - 15.25) < 0.05
     finally:
         E.set_conv_precision(old)
+
+
+def test_async_encode_beside_a_decode_gives_the_same_bytes():
+    """encode_batch_begin on the side stream (its own SM partition where the driver offers one) while
+    another batch is being decoded: same containers as the synchronous call, lossless both ways."""
+    import l3c_pytorch_b200 as l3c
+    bp = util.blueprint('cr')
+    bc = l3c.Bitcoding(bp)
+    a = torch.stack([util.make_image(i, 128, 128) for i in range(4)])
+    b = torch.stack([util.make_image(10 + i, 128, 128) for i in range(4)])
+    datas_a, _ = bc.encode_batch(a)
+    want_b, bpsp_b = bc.encode_batch(b)
+    side = bc.side_stream(a.shape[0])
+    job = bc.encode_batch_begin(b.pin_memory(), stream=side)         # enqueued, not waited for
+    dec_a = bc.decode_batch(datas_a)                                  # runs beside it
+    got_b, bpsp_b2 = job.finish()
+    assert got_b == want_b and bpsp_b2 == bpsp_b
+    for i in range(4):
+        assert torch.equal(dec_a[i][0].cpu(), a[i].long())
+    dec_b = bc.decode_batch(got_b)
+    for i in range(4):
+        assert torch.equal(dec_b[i][0].cpu(), b[i].long())
+    # several jobs in flight on the same stream finish in any order
+    jobs = [bc.encode_batch_begin(x, stream=side) for x in (a, b)]
+    assert jobs[1].finish()[0] == want_b and jobs[0].finish()[0] == datas_a
+
+
+def test_sm_partition_streams_run_kernels_and_report_group_sizes():
+    """l3c_partition_streams: two disjoint SM groups; a kernel launched into either gives the same
+    result as on an ordinary stream.  Skipped where the driver has no green contexts."""
+    from l3c_pytorch_b200 import engine as E
+    dev = torch.device('cuda', torch.cuda.current_device())
+    part = E.partition_streams(dev, 24, 3, 4)
+    if part is None:
+        pytest.skip('driver cannot partition SMs (L3C_EUNSUPPORTED)')
+    s_a, s_b, n_a, n_b = part
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    assert len(s_a) == 3 and len(s_b) == 4 and n_a >= 24 and n_b >= 8 and n_a + n_b <= n_sm
+    assert E.partition_streams(dev, 24, 3, 4)[0][0].cuda_stream == s_a[0].cuda_stream     # cached, not re-created
+    bp = util.blueprint('cr')
+    conv = bp.net.nets[0].enc.body[0].body[0]
+    x = torch.randn(2, 64, 64, 64, device=dev)
+    old = E.get_conv_precision()
+    E.set_conv_precision('tf32')
+    try:
+        want = E.conv2d(conv, x)
+        torch.cuda.synchronize()
+        for st in (s_a[0], s_b[0], s_b[3]):
+            with torch.cuda.stream(st):
+                got = E.conv2d(conv, x)                      # persistent grid sized to the group
+            st.synchronize()
+            assert torch.equal(got, want)
+    finally:
+        E.set_conv_precision(old)
