@@ -9,10 +9,15 @@
 //     can only ever visit them in that order);
 //   * the encoder consumes pre-computed 32-bit (c_low, c_high-1) intervals (one coalesced load per
 //     32 symbols) instead of indexing a CDF table with the symbol;
+//   * the encoder keeps bit emission off its serial chain: per symbol only (low, k, u) is recorded,
+//     every 32 symbols the warp packs the 32 bit strings in parallel (one packed scan);
 //   * the decoder replaces the per-row binary search by a warp-wide comparison of the whole CDF row
-//     against the scaled code value (no division: cdf[m]*span < (value-low+1)<<16  <=>
-//     cdf[m] <= ((value-low+1)*2^16-1)/span), followed by warp max/min/add reductions (REDUX);
-//     rows are prefetched 8 symbols ahead so HBM latency stays off the serial dependency chain;
+//     against the code value (no division: cdf[m] <= ((value-low+1)*2^16-1)/span  <=>
+//     mulhi(cdf[m] << 16, span) <= value - low) and one warp max-reduction over packed
+//     (cdf[m], cdf[m+1]-1) proposals; rows are prefetched one to two groups of 8 symbols ahead so
+//     HBM latency stays off the serial dependency chain;
+//   * coder state is (low, r = high - low[, dv = value - low]): every renormalisation shift maps
+//     r -> 2r+1, dv -> 2dv+bit, so `high`, `value` and the MSB fix-ups leave the chain;
 //   * coder state can be saved/restored so that a stream may be decoded in chunks while later CDF
 //     rows are still being built (RGB channel pipelining).
 #include "common.cuh"
@@ -697,11 +702,14 @@ ac_decode32_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, 
 //                 the packed proposal (cdf[m] << 16) | (cdf[m+1] - 1) and stores the row in a shared
 //                 memory ring; later turns the decoder's winning proposals into symbol indices
 //                 (number of proposals <= winner, minus 1) and writes them out.
-//   decoder warp: computes the reference's `count` exactly (float estimate + 64-bit integer
-//                 correction, no division), compares its 8 proposals against (count << 16 | 0xFFFF)
-//                 with ONE integer compare each, takes ONE warp max-reduction (rows are sorted, so
-//                 the last proposal whose cdf[m] <= count is the largest) and gets both interval
-//                 bounds from it; then the usual update / clz renormalisation / bit refill.
+//   decoder warp: per lane eight compares  mulhi(cdf[m] << 16, span) <= value - low  (no division: this
+//                 is cdf[m] <= count of torchac.cpp:327), ONE warp max-reduction (rows are sorted,
+//                 so the last passing proposal is the largest) that yields both interval bounds,
+//                 then the update / clz renormalisation / funnel-shift refill on (low, r, dv).
+//                 Groups of 8 symbols run as straight-line SPECULATIVE code: the two events that
+//                 cannot occur on a valid stream (code value outside [low, high], > 32 shifts) and
+//                 the 2^32 span of a stream's first symbol only set a sticky flag, after which the
+//                 group is replayed from a checkpoint by the exact, branchy path.
 // Hand-over by two mbarrier pairs (full/empty per group of 8 ring slots).
 // ---------------------------------------------------------------------------------------------
 namespace v3 {
@@ -727,22 +735,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
     } while (!done);
-}
-
-// count = ((value - low + 1) * 2^16 - 1) / span, exact, for value in [low, high]  (torchac.cpp:327):
-// float estimate (within 1 of the quotient) + one 64-bit integer correction, no division.
-// (Searching with the raw estimate and verifying the found interval afterwards was measured slower.)
-__device__ __forceinline__ uint32_t exact_count(uint32_t dv, uint32_t r) {
-    const uint64_t num = ((uint64_t)dv << 16) | 0xFFFFull;           // (dv+1)*65536 - 1
-    const float x = __uint2float_rn(dv) + 1.0f;
-    const float y = __uint2float_rn(r) + 1.0f;
-    float inv;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(y));
-    uint32_t q = __float2uint_rz(x * inv * 65536.0f);                // may be 65536 when dv == r
-    const uint64_t prod = (uint64_t)q * r + q;                       // q * span
-    const uint64_t span = (uint64_t)r + 1ull;
-    q = q - (prod > num ? 1u : 0u) + ((prod <= num && num - prod >= span) ? 1u : 0u);
-    return q;
 }
 
 __global__ void __launch_bounds__(64)
