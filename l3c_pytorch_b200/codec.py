@@ -325,7 +325,15 @@ class BatchCodec(object):
         cache = self.__dict__.setdefault('_rgb_stream_cache', {})
         if key not in cache:
             part = None
-            if os.environ.get('L3C_SM_PARTITION', '1') != '0':
+            want_part = os.environ.get('L3C_SM_PARTITION', '1') != '0'
+            if want_part and os.environ.get('CUDA_INJECTION64_PATH') and 'L3C_SM_PARTITION' not in os.environ:
+                # Nsight Compute cannot profile kernels launched into green-context streams (it lost the
+                # process at the first one): under a CUDA injection tool use ordinary streams
+                import sys
+                print('l3c_pytorch_b200: profiler injection detected, SM partitions off '
+                      '(set L3C_SM_PARTITION=1 to force them)', file=sys.stderr)
+                want_part = False
+            if want_part:
                 n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
                 # two decoder CTAs per SM (measured at 16 x 512^2: 48 / 24 / 16 SMs -> decode 95 / 86 / 93 ms)
                 want = min(max(8, -(-n_decoders // 16) * 8), (n_sm // 16) * 8)
