@@ -254,14 +254,26 @@ def run_ours(args):
         main_stream.wait_stream(cur)
         side_stream.wait_stream(cur)
         job = bc.encode_batch_begin(host_sets[first_set % n_sets], stream=side_stream)
+        # the decoded images come back through two pinned buffers; the read-back of step s is awaited
+        # after step s+1 has been issued, so the host prepares the next decode while this one runs
+        bufs = [torch.empty_like(host_sets[0]).pin_memory() for _ in range(2)]
+        pending = None
+        back = None
         for s in range(steps):
             datas, _ = job.finish()
             job = None
             if s + 1 < steps:
                 job = bc.encode_batch_begin(host_sets[(first_set + s + 1) % n_sets], stream=side_stream)
             with torch.cuda.stream(main_stream):
-                dec = bc.decode_batch(datas)
-                back = torch.cat(dec, 0).to(torch.uint8).cpu()    # D2H of the result
+                dec = bc.decode_batch(datas)                   # containers -> GPU -> images (asynchronous)
+                bufs[s % 2].copy_(torch.cat(dec, 0).to(torch.uint8), non_blocking=True)    # D2H of the result
+                ev = torch.cuda.Event()
+                ev.record(main_stream)
+            if pending is not None:
+                pending.synchronize()
+            pending = ev
+        pending.synchronize()
+        back = bufs[(steps - 1) % 2]
         cur.wait_stream(main_stream)
         cur.wait_stream(side_stream)
         return back, datas
