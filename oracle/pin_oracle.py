@@ -41,6 +41,27 @@ def main():
             junk = bytes(rng.integers(0, 256, size=max(1, len(want) // 2)).astype(np.uint8))
             assert (ac.decode(cdf, junk) == ref.decode_cdf(t_cdf, junk).numpy()).all()
             n_cases += 1
+    # long underflow runs: every symbol straddles the midpoint, the owed ("pending") bits pile up far
+    # beyond 32 and across many symbols before a release or the terminator flushes them
+    # (torchac.cpp:196-206, 209-219) -- the path the GPU encoder's batched emission must reproduce
+    n_under = 0
+    for n_sym in (5, 33, 1000, 4099):
+        for trial in range(3):
+            half = 32768
+            rows = np.zeros((n_sym, 4), np.int64)
+            for i in range(n_sym):
+                rows[i, :3] = [0, half - int(rng.integers(1, 200)), half + int(rng.integers(1, 200))]
+            sym = np.ones(n_sym, np.int16)
+            if trial < 2:
+                for i in rng.integers(0, n_sym, size=max(1, n_sym // 37)):
+                    sym[i] = int(rng.integers(0, 3))
+            cdf = rows.astype(np.uint16)
+            t_cdf = torch.from_numpy(cdf.view(np.int16).copy()).reshape(1, 1, n_sym, 4)
+            want = ref.encode_cdf(t_cdf, torch.from_numpy(sym.copy()))
+            assert ac.encode(cdf, sym) == want, ('underflow', n_sym, trial)
+            assert (ac.decode(cdf, want) == ref.decode_cdf(t_cdf, want).numpy()).all()
+            n_under += 1
+    n_cases += n_under
     # KATs
     row25 = ac.uniform_cdf_row(25)
     assert row25.tolist()[:4] == [0, 2621, 5243, 7864] and row25[-1] == 0 and row25[-2] == 62915
@@ -49,7 +70,8 @@ def main():
     assert ac.encode(row256, np.array([0, 255, 128, 1, 254, 77], np.int16)).hex() == '00ff8001fe4d40'
     assert ac.encode(row25, np.array([0], np.int16)).hex() == '04'
     assert ac.encode(row25, np.array([24], np.int16)).hex() == 'f8'
-    print('pinned: %d random cases + KAT1/1b/3 byte-identical to oracle/_ref' % n_cases)
+    print('pinned: %d random cases (incl. %d long-underflow ones) + KAT1/1b/3 byte-identical to oracle/_ref'
+          % (n_cases, n_under))
     return 0
 
 

@@ -191,3 +191,38 @@ def test_no_cpu_fallback_on_cpu_tensors():
         bp.net(torch.zeros(1, 3, 32, 32))
     with pytest.raises(ValueError):
         engine.conv2d(bp.net.heads[1].head, torch.zeros(1, 8, 8, 64))
+
+
+def test_coder_state_and_batched_emission_models_match_the_oracle():
+    """The (low, r) state with the collapsed renormalisation and the order-free, per-32-symbol bit
+    emission of ac_encode_kernel, modelled in Python, reproduce the oracle's (= the reference's) bytes --
+    including owed-bit runs that cross batches and exceed 32 (the kernel's sequential-sink case)."""
+    from oracle import ac
+    from tests import kernel_models as km
+    rng = np.random.default_rng(11)
+    cases = []
+    for L, n in [(25, 1), (25, 200), (256, 333), (3, 97)]:
+        w = rng.integers(1, 4000, size=(n, L)).astype(np.float64)
+        w = w / w.sum(1, keepdims=True) * (65536 - L - 41)
+        c = np.floor(np.cumsum(w, 1)).astype(np.int64) + np.arange(1, L + 1)
+        cdf = np.concatenate([np.zeros((n, 1), np.int64), c[:, :-1], np.zeros((n, 1), np.int64)], 1).astype(np.uint16)
+        cases.append((cdf, rng.integers(0, L, size=n).astype(np.int16)))
+    for n in (5, 33, 64, 400):                                   # long underflow runs
+        rows = np.zeros((n, 4), np.int64)
+        for i in range(n):
+            rows[i, :3] = [0, 32768 - int(rng.integers(1, 200)), 32768 + int(rng.integers(1, 200))]
+        sym = np.ones(n, np.int16)
+        sym[rng.integers(0, n, size=max(1, n // 37))] = 0
+        cases.append((rows.astype(np.uint16), sym))
+        cases.append((rows.astype(np.uint16), np.ones(n, np.int16)))
+    for cdf, sym in cases:
+        L = cdf.shape[1] - 1
+        iv = []
+        for i, s_ in enumerate(sym):
+            hi = 65536 if s_ == L - 1 else int(cdf[i, s_ + 1])
+            iv.append((int(cdf[i, s_]), hi))
+        recs, final_low = km.coder_records(iv)
+        data = ac.encode(cdf, sym)
+        assert km.emit_batched(recs, final_low) == data
+        # and the decoders' (low, r, dv) state with the division-free search reads it back
+        assert (km.decode_model(cdf, data, len(sym)) == sym).all()
