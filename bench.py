@@ -7,10 +7,12 @@
 One "step" = one lossless round trip (encode -> decode) of one batch of synthetic 3x512x512 images
 per GPU (BASELINE.json configs[1]: 16 images per GPU, L3C cr.cf, seed-0 default-init weights).
 Prints ONE JSON line (rank 0).  `value` = Mpixels/s with inputs resident in HBM; `e2e` = the same
-round trip through the public `Bitcoding.encode_batch/decode_batch` API from pinned host buffers
-(H2D of the images and the containers, D2H of the containers and the decoded images inside the
-timed region).  Timing: CUDA events on the launching stream, barrier + synchronize on both sides,
-max over ranks.
+round trip through the public `Bitcoding.encode_batch[_begin]/decode_batch` API from pinned host
+buffers (H2D of the images and the containers, D2H of the containers and the decoded images inside
+the timed region).  By default the K steps are software-pipelined (the encode of batch k+1 runs beside
+the latency-bound decode of batch k); the strictly sequential figures are reported beside them
+(`sequential`, `e2e.sequential_value`) and `--no-pipeline` makes them the headline.  Timing: CUDA events
+on the stream all work forks from and joins, barrier + synchronize on both sides, max over ranks.
 """
 import argparse
 import json
@@ -405,7 +407,7 @@ def run_ours(args):
 
     # ---- where the step goes (one extra, untimed-for-the-metric round trip with CUDA events): the
     #      dominant kernel by time is the serial range decoder, which is latency-bound (one warp per
-    #      stream, ~280 ns per symbol whatever the number of streams), not HBM- or tensor-bound
+    #      stream, ~180 ns per symbol whatever the number of streams), not HBM- or tensor-bound
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     torch.cuda.synchronize()
     ev[0].record()
