@@ -46,6 +46,17 @@ class MultiscaleBlueprint(nn.Module):
         nonrecursive_bpsps = costs_bpsp[:out.auto_recursive_from] + [final_cost_uniform / conversion]
         return MultiscaleLoss(sum(costs_bpsp), nonrecursive_bpsps, None)
 
+    def get_loss_per_image(self, out: Out, num_subpixels_before_pad=None):
+        """Total theoretical bpsp (all scales + the uniform-prior final scale) of every image of the
+        batch, as a list of floats: what get_loss() gives for a batch of one, without running the
+        images one at a time.  `num_subpixels_before_pad` counts ONE image."""
+        costs, final_cost_uniform, num_subpixels = self.losses.get_per_image(out)
+        if num_subpixels_before_pad:
+            assert num_subpixels_before_pad <= num_subpixels, num_subpixels_before_pad
+            num_subpixels = num_subpixels_before_pad
+        total = sum(costs) + final_cost_uniform                  # numpy float64 [N]
+        return (total / (np.log(2.) * num_subpixels)).tolist()
+
     @staticmethod
     def unpack_batch_pad(raw, fac):
         if len(raw.shape) == 3:

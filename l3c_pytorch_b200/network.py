@@ -315,6 +315,16 @@ class Losses(nn.Module):
         final_idx = -1 if out.auto_recursive_from is None else out.auto_recursive_from
         return costs, out.get_nat_count(final_idx), int(np.prod(out.S_u8[0].shape))
 
+    def get_per_image(self, out):
+        """Same quantities as get(), kept apart per image of the batch: (per-scale nats as float64
+        arrays [N], uniform-scale nats of ONE image, sub-pixels of ONE image)."""
+        costs = [self.loss_dmol_rgb.nll_sum(out.S_u8[0], out.P_nhwc[0]).double().cpu().numpy()]
+        for s in range(1, len(out.P_nhwc)):
+            costs.append(self.loss_dmol_n.nll_sum(out.S_u8[s], out.P_nhwc[s]).double().cpu().numpy())
+        final_idx = -1 if out.auto_recursive_from is None else out.auto_recursive_from
+        n = out.S_u8[0].shape[0]
+        return costs, out.get_nat_count(final_idx) / n, int(np.prod(out.S_u8[0].shape[1:]))
+
 
 class MultiscaleNetwork(nn.Module):
     def __init__(self, config_ms):
