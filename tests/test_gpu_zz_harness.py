@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 def _png(path, h, w, seed):
     from PIL import Image
-    Image.fromarray(util.make_image(seed, h, w).permute(1, 2, 0).numpy()).save(path)
+    Image.fromarray(util.make_image(seed, h, w).permute(1, 2, 0).contiguous().numpy()).save(path)
 
 
 def test_harness_theory_and_write_to_files(tmp_path, capsys):
