@@ -77,7 +77,7 @@ def decode_model(cdf, data, n_sym):
     """Decoder with the kernels' state (low, r, dv = value - low): per symbol the passing entries are
     those with mulhi(cdf[m] << 16, r + 1) <= dv (no division; equals cdf[m] <= count of
     torchac.cpp:327), the update is width/low as in coder_records and dv' = ((dv - lo16) << s) | next s
-    code bits.  Valid streams only (the kernels replay anything else through the exact path)."""
+    code bits.  A code value outside [low, high] takes the reference's modular count (the kernels' replay path)."""
     bits = ''.join(format(b, '08b') for b in data)
     pos = [0]
 
@@ -92,8 +92,14 @@ def decode_model(cdf, data, n_sym):
     L = cdf.shape[1] - 1
     for i in range(n_sym):
         span = r + 1
-        assert dv <= r
-        passing = [m for m in range(L) if ((int(cdf[i, m]) << 16) * span) >> 32 <= dv]
+        if dv <= r:
+            passing = [m for m in range(L) if ((int(cdf[i, m]) << 16) * span) >> 32 <= dv]
+        else:
+            # code value outside [low, high] (garbage / foreign input): the reference's count in its
+            # modular 64-bit arithmetic (torchac.cpp:327), as the kernels' replay path computes it
+            off = ((low + dv) & M32) - low + 1
+            count = ((((off & 0xFFFFFFFFFFFFFFFF) * 65536 - 1) & 0xFFFFFFFFFFFFFFFF) // span) & 0xFFFF
+            passing = [m for m in range(L) if int(cdf[i, m]) <= count]
         m = passing[-1] if passing else 0
         out.append(m)
         if i == n_sym - 1:

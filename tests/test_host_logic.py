@@ -226,3 +226,6 @@ def test_coder_state_and_batched_emission_models_match_the_oracle():
         assert km.emit_batched(recs, final_low) == data
         # and the decoders' (low, r, dv) state with the division-free search reads it back
         assert (km.decode_model(cdf, data, len(sym)) == sym).all()
+        # garbage / truncated input: same symbols as the oracle (= the compiled reference, pin_oracle.py)
+        junk = bytes(rng.integers(0, 256, size=max(1, len(data) // 2)).astype(np.uint8))
+        assert (km.decode_model(cdf, junk, len(sym)) == ac.decode(cdf, junk)).all()
