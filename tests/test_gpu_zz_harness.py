@@ -1,7 +1,8 @@
 """GPU: the test harness end to end on a throw-away experiment directory:
 seed-0 weights saved as a reference-format checkpoint, three PNGs (two of equal size, one that needs
 padding), default (theoretical bpsp, batched) mode against the one-image-at-a-time path, then
---write_to_files through the real coder."""
+--write_to_files through the real coder.  (The file name sorts after the hot-path suites on purpose:
+the harness is a caller of the path, its test runs once the path itself is green.)"""
 import os
 
 import numpy as np
