@@ -2,17 +2,20 @@
 """bench.py -- headline benchmark of the L3C encode/decode hot path (see BASELINE.json).
 
   python bench.py --gpus N --steps K --warmup W                 (our sm_100a path, one process per GPU)
-  python bench.py --impl reference --gpus N --steps K --warmup W (reference CPU path, host cores)
+  python bench.py --impl reference --gpus N --steps K --warmup W (reference CPU algorithm, host cores)
+  python bench.py --workload rgb_shared | crops                  (BASELINE configs 4 and 5; default: 2/3)
 
-One "step" = one lossless round trip (encode -> decode) of one batch of synthetic 3x512x512 images
-per GPU (BASELINE.json configs[1]: 16 images per GPU, L3C cr.cf, seed-0 default-init weights).
+One "step" = one lossless round trip (encode -> decode) of one batch of synthetic images per GPU:
+  l3c         16 x 3x512x512, L3C cr.cf                 (BASELINE configs[1] at N=1, configs[2] at N=8)
+  rgb_shared  32 x 3x256x256, cr_rgb_shared.cf, fp32    (configs[3])
+  crops       1 x 3x3000x2000 per GPU -> 4 crops of 1500x1000 padded to 1504x1000 (configs[4], --gpus 4)
 Prints ONE JSON line (rank 0).  `value` = Mpixels/s with inputs resident in HBM; `e2e` = the same
-round trip through the public `Bitcoding.encode_batch[_begin]/decode_batch` API from pinned host
-buffers (H2D of the images and the containers, D2H of the containers and the decoded images inside
-the timed region).  By default the K steps are software-pipelined (the encode of batch k+1 runs beside
-the latency-bound decode of batch k); the strictly sequential figures are reported beside them
-(`sequential`, `e2e.sequential_value`) and `--no-pipeline` makes them the headline.  Timing: CUDA events
-on the stream all work forks from and joins, barrier + synchronize on both sides, max over ranks.
+round trip through the public `Bitcoding` API from pinned host buffers (H2D of the images and the
+containers, D2H of the containers and the decoded images inside the timed region).  By default the K
+steps are software-pipelined (the encode of batch k+1 runs beside the latency-bound decodes of earlier
+batches); the strictly sequential figures are reported beside them (`sequential`,
+`e2e.sequential_value`) and `--no-pipeline` makes them the headline.  Timing: CUDA events on the stream
+all work forks from and joins, barrier + synchronize on both sides, max over ranks.
 """
 import argparse
 import json
@@ -27,17 +30,30 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = 'Mpixels/s encode+decode (lossless round-trip)'
-IMAGES_PER_GPU = 16
-HW = 512
-CONV_FLOP_PER_PX_ROUNDTRIP = 2.230e6      # 1.368 (encode forward) + 0.863 (decode)
+
+# conv FLOPs per pixel of a round trip: encode forward + decoder-side re-run
+WORKLOADS = {
+    'l3c': dict(cfg='cr', n_img=16, H=512, W=512, precision='tf32', golden='l3c_512x512',
+                flop_per_px=2.230e6,
+                name='L3C cr.cf (3 scales, seed-0 default init), %d x 3x512x512 uint8 noise images per GPU, '
+                     'encode+decode round trip, byte-compatible .l3c containers'),
+    'rgb_shared': dict(cfg='cr_rgb_shared', n_img=32, H=256, W=256, precision='fp32', golden='rgbs_256x256',
+                       flop_per_px=1.309e6,
+                       name='RGB-shared baseline cr_rgb_shared.cf (bicubic thumbnail + 1 scale), %d x 3x256x256 '
+                            'uint8 noise images per GPU, encode+decode round trip'),
+    'crops': dict(cfg='cr', n_img=1, H=3000, W=2000, precision='tf32', golden=None, flop_per_px=2.230e6,
+                  name='L3C cr.cf, adaptive-crop path: %d x 3x3000x2000 uint8 noise image per GPU -> 4 crops of '
+                       '1500x1000 (auto_crop) padded to 1504x1000, coded as one batch, decoded and stitched'),
+}
 
 
-def make_images(first, n, hw=HW):
+def make_images(first, n, h, w=None):
     import torch
+    w = h if w is None else w
     out = []
     for i in range(first, first + n):
         g = torch.Generator().manual_seed(1000 + i)
-        out.append((torch.rand(3, hw, hw, generator=g) * 255).round().to(torch.uint8))
+        out.append((torch.rand(3, h, w, generator=g) * 255).round().to(torch.uint8))
     return torch.stack(out)
 
 
@@ -92,68 +108,106 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU algorithm on the host cores
+# reference arm: the reference's CPU algorithm on the host cores.  NOTHING of the product package is
+# imported in this arm (nor in its worker processes): weights come from oracle/weights.py (plain torch
+# module tree, same seeded default init as the reference), the algorithm from oracle/model.py.
 # ------------------------------------------------------------------------------------------------
-def cpu_roundtrip_mpx_s(n_images, hw, first_image=0):
-    """Round trip of `n_images` hw x hw images with the reference's CPU algorithm as restated in
-    oracle/model.py (byte-identical to the unmodified reference on the golden fixtures): PyTorch
-    fp32 CPU convs (all host threads), PyTorch CPU CDF tables (torchac.py:174-213), the reference's
-    own coder loop.  Returns (Mpx/s, seconds, bpsp, threads)."""
+_REF = {}
+
+
+def _ref_init(threads):
     import torch
-    from l3c_pytorch_b200 import config
-    from l3c_pytorch_b200.blueprint import MultiscaleBlueprint
-    from oracle import model as om
-    try:        # torchrun pins OMP_NUM_THREADS=1: give the CPU reference the physical cores it may use;
-        # otherwise keep PyTorch's own default (measured faster than one thread per SMT sibling)
-        if torch.get_num_threads() == 1:
-            torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) // 2))
-    except (AttributeError, RuntimeError):
-        pass
-    torch.manual_seed(0)
-    bp = MultiscaleBlueprint(config.ms_config('cr'), device='cpu')
-    sd = {k: v.detach().cpu() for k, v in bp.net.state_dict().items()}
-    imgs = make_images(first_image, n_images, hw)
+    torch.set_num_threads(max(1, threads))
+    torch.set_grad_enabled(False)
+
+
+def _ref_roundtrip(task):
+    """One lossless round trip of ONE image with the reference's CPU algorithm as restated in
+    oracle/model.py (byte-identical to the unmodified reference on the golden fixtures): PyTorch fp32 CPU
+    convs, PyTorch CPU CDF tables (torchac.py:174-213), the reference's coder loop.  -> (bytes, seconds)"""
+    workload, seed_idx, h, w = task
+    import torch
+    from oracle import model as om, weights
+    cfg = om.CFG_RGB_SHARED if workload == 'rgb_shared' else om.CFG_L3C
+    if workload not in _REF:
+        _REF[workload] = weights.default_init_state_dict(cfg)
+    sd = _REF[workload]
+    img = make_images(seed_idx, 1, h, w)[0]
     t0 = time.perf_counter()
-    total_bytes = 0
     with torch.no_grad():
-        for i in range(n_images):
-            data = om.encode_image(sd, om.CFG_L3C, imgs[i], 'torch')
-            dec = om.decode_image(sd, om.CFG_L3C, data, 'torch')
-            assert bool((dec[0] == imgs[i].long()).all()), 'CPU reference round trip not lossless'
-            total_bytes += len(data)
+        data = om.encode_image(sd, cfg, img, 'torch')
+        dec = om.decode_image(sd, cfg, data, 'torch')
     dt = time.perf_counter() - t0
-    px = n_images * hw * hw
-    return px / 1e6 / dt, dt, total_bytes * 8 / (3 * px), torch.get_num_threads()
+    assert bool((dec[0] == img.long()).all()), 'CPU reference round trip not lossless'
+    return len(data), dt
+
+
+def _host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _reference_sample(workload):
+    """(h, w, description) of the bounded per-step sample of the reference arm."""
+    wl = WORKLOADS[workload]
+    if workload == 'crops':
+        # one 1504x1000 crop needs ~15 GB of CDF temporaries per channel on the CPU path: time the same
+        # algorithm on one 512x512 tile instead (its per-pixel rate is size-stable to ~2 %)
+        return 512, 512, 'one 3x512x512 tile (of a 1504x1000 crop) per step'
+    return wl['H'], wl['W'], 'one 3x%dx%d image of the %d-image batch per step' % (wl['H'], wl['W'], wl['n_img'])
+
+
+def cpu_roundtrips(workload, n_tasks, n_warm, first_seed=0):
+    """`n_tasks` independent round trips on ALL host cores: a pool of P worker processes with
+    cores/P torch threads each (the CPU path is bound by its PyTorch CDF materialisation, which scales
+    poorly past ~8 threads; independent images in parallel is how the reference would use a big host).
+    Returns dict(value Mpx/s, seconds, cores, workers, threads, bpsp, sample)."""
+    import multiprocessing as mp
+    h, w, sample = _reference_sample(workload)
+    cores = _host_cores()
+    workers = max(1, min(8, cores // 8, n_tasks))
+    threads = max(1, cores // workers)
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(workers, initializer=_ref_init, initargs=(threads,)) as pool:
+        if n_warm:
+            pool.map(_ref_roundtrip, [(workload, first_seed + i, h, w) for i in range(n_warm)])
+        t0 = time.perf_counter()
+        res = pool.map(_ref_roundtrip, [(workload, first_seed + i, h, w) for i in range(n_tasks)], chunksize=1)
+        dt = time.perf_counter() - t0
+    px = n_tasks * h * w
+    return {'value': px / 1e6 / dt, 'seconds': dt, 'cores': workers * threads, 'workers': workers,
+            'threads_per_worker': threads, 'bpsp': sum(r[0] for r in res) * 8.0 / (3 * px),
+            'mean_image_seconds': sum(r[1] for r in res) / n_tasks, 'sample': sample}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
-    import torch
+    wl = WORKLOADS[args.workload]
     steps, warm = args.steps, args.warmup
-    hw = HW if (steps + warm) <= 6 else 256          # keep the whole run within a few minutes
-    for _ in range(warm):
-        cpu_roundtrip_mpx_s(1, 128)
-    vals = []
-    t_all = 0.0
-    for s in range(steps):
-        v, dt, bpsp, thr = cpu_roundtrip_mpx_s(1, hw, first_image=s)
-        vals.append(v)
-        t_all += dt
-    px = steps * hw * hw
-    value = px / 1e6 / t_all
+    cores = _host_cores()
+    workers = max(1, min(8, cores // 8, steps))
+    # warm-up: every worker imports torch and runs the real sample once (at most one wave)
+    r = cpu_roundtrips(args.workload, steps, min(warm, workers))
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'Mpixels/s', 'n_gpus': args.gpus,
-        'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * t_all / steps, 'higher_is_better': True,
+        'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': 'Mpixels/s', 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * r['seconds'] / steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'L3C cr.cf, %d x 3x512x512 per GPU, encode+decode round trip' % IMAGES_PER_GPU,
-                   'sample': '1 image of 3x%dx%d per step on the host CPU' % (hw, hw)},
-        'cpu_baseline': {'value': value, 'unit': 'Mpixels/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-                         'sample': '%d round trip(s) of one 3x%dx%d image (oracle/model.py, PyTorch-CPU CDF path, '
-                                   'byte-identical to the unmodified reference on tests/golden)' % (steps, hw, hw)},
-        'e2e': {'value': value, 'unit': 'Mpixels/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'bpsp': bpsp,
+        'config': {'workload': wl['name'] % wl['n_img'], 'bench_workload': args.workload,
+                   'sample': '%s; steps run %d at a time on a pool of %d worker processes x %d torch threads '
+                             '(= all %d host cores); warm-up = %d such round trip(s)'
+                             % (r['sample'], r['workers'], r['workers'], r['threads_per_worker'], r['cores'],
+                                min(warm, workers))},
+        'cpu_baseline': {'value': r['value'], 'unit': 'Mpixels/s', 'cores': r['cores'], 'kind': 'port',
+                         'sample': '%d round trip(s), %s: oracle/model.py with the reference\'s PyTorch-CPU CDF path '
+                                   '(byte-identical to the unmodified reference on tests/golden), weights from '
+                                   'oracle/weights.py; %.1f s per image per worker'
+                                   % (steps, r['sample'], r['mean_image_seconds'])},
+        'e2e': {'value': r['value'], 'unit': 'Mpixels/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'bpsp': r['bpsp'],
     }
     print(json.dumps(line))
     return 0
@@ -162,31 +216,61 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def _profile_json(name):
+    try:
+        with open(os.path.join(ROOT, 'profiles', name)) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     import l3c_pytorch_b200 as l3c
-    from l3c_pytorch_b200 import config, dist as l3c_dist, engine as E, _lib
+    from l3c_pytorch_b200 import auto_crop, config, dist as l3c_dist, engine as E, pad as l3c_pad
 
+    wl = WORKLOADS[args.workload]
+    precision = args.precision or wl['precision']
     rank, world, local_rank = l3c_dist.init_from_env()
     assert torch.cuda.is_available(), 'bench.py (our arm) needs a GPU; there is no CPU fallback'
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
-    E.set_conv_precision(args.precision)
+    E.set_conv_precision(precision)
     torch.manual_seed(0)
-    bp = l3c.MultiscaleBlueprint(config.ms_config('cr'), device=dev).set_eval()
+    bp = l3c.MultiscaleBlueprint(config.ms_config(wl['cfg']), device=dev).set_eval()
     bc = l3c.Bitcoding(bp)
     codec = bc.codec
-    n_img = args.images_per_gpu
+    n_img = args.images_per_gpu or wl['n_img']
     n_global = n_img * world
     lo, hi = l3c_dist.shard_bounds(n_global, rank, world)
-    # a few distinct batches so consecutive steps do not see identical inputs; activations are
-    # ~1 GB per layer at this batch size, far beyond the 126 MB L2
+    H, W = wl['H'], wl['W']
+    fac = 2 ** bp.net.config_ms.num_scales
+    crops_mode = args.workload == 'crops'
+
+    # a few distinct batches so consecutive steps do not see identical inputs; activations are ~1 GB per
+    # layer at these batch sizes, far beyond the 126 MB L2
     n_sets = 2
-    host_sets = [make_images(lo + s * n_global, n_img).pin_memory() for s in range(n_sets)]
+    raw_sets = [make_images(lo + s * n_global, n_img, H, W) for s in range(n_sets)]      # [n_img,3,H,W] uint8
+
+    def to_batch(raw):
+        """host-side shape plumbing (auto_crop.py:44-75, pad.py:23-59): -> (uint8 batch, pad tuple)"""
+        if not crops_mode:
+            return raw, (0, 0, 0, 0)
+        parts = []
+        for i in range(raw.shape[0]):
+            parts.extend(auto_crop.iter_crops(raw[i:i + 1]))
+        pt = l3c_pad.padding_tuple(parts[0].shape[-2], parts[0].shape[-1], fac)
+        return torch.nn.functional.pad(torch.cat(parts, 0), pt, 'constant').contiguous(), pt
+
+    batches = [to_batch(r) for r in raw_sets]
+    pad_tuple = batches[0][1]
+    host_sets = [b.pin_memory() for (b, _) in batches]
     dev_sets = [h.to(dev) for h in host_sets]
-    launches = {'n': 0}
+    n_units = host_sets[0].shape[0]                      # images (or crops) per step per GPU
+    Hp, Wp = host_sets[0].shape[-2:]
+    px_step_global = n_global * H * W                    # unpadded pixels: what the user handed in
 
     def barrier():
         if world > 1:
@@ -194,26 +278,43 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def shapes_of(info):
-        return [(C, H, W) for (_, C, H, W) in info['shapes']]
+        return [(C, h, w) for (_, C, h, w) in info['shapes']]
 
     def step_resident(imgs):
-        blob, info = codec.encode_batch(imgs, to_host=False)
+        blob, info = codec.encode_batch(imgs, pad_tuple, to_host=False)
         S = codec.decode_device(blob, info['stream_offsets'], info['lens'], shapes_of(info))
         return S, info
 
-    def step_e2e(host_imgs):
-        datas, bpsps = bc.encode_batch(host_imgs)
+    tmpdir = None
+    if crops_mode:
+        import tempfile
+        tmpdir = tempfile.mkdtemp(prefix='l3c_bench_', dir='/dev/shm' if os.path.isdir('/dev/shm') else None)
+
+    def step_e2e(k):
+        """the call a user makes.  l3c / rgb_shared: Bitcoding.encode_batch -> decode_batch from pinned host
+        buffers; crops: Bitcoding.encode(img, file) -> .part0..3 -> Bitcoding.decode(file) (the reference's
+        file API, auto_crop + pad + stitch inside), files on a RAM disk."""
+        if crops_mode:
+            outs = []
+            for i in range(n_img):
+                p = os.path.join(tmpdir, 'r%d_i%d.l3c' % (rank, i))
+                for q in l3c.part_suffix_helper.existing_parts(p):
+                    os.remove(q)
+                bc.encode(raw_sets[k][i].long(), p)
+                outs.append(bc.decode(p + '.part0').to(torch.uint8).cpu())
+            return torch.cat(outs, 0), None
+        datas, bpsps = bc.encode_batch(host_sets[k])
         dec = bc.decode_batch(datas)
         back = torch.cat(dec, 0).to(torch.uint8).cpu()        # D2H of the result
         return back, datas
 
-    # Software pipelining over steps (the default): the decode of a batch is bound by the serial range
-    # decoder and leaves most SMs idle, so the encode of the NEXT batch runs beside it, on a stream that
-    # is confined to the SMs the decoders do not own.  K complete round trips -- including the
-    # un-overlapped first encode and last decode -- lie inside the timed region.
-    side_stream = codec.encode_stream(dev, 3 * n_img)
-    # the decode is the latency-critical half: it runs on a high-priority stream so that its kernels
-    # are scheduled ahead of the encode's whenever both are waiting for SMs
+    # Software pipelining over steps (the default): a decode is bound by the serial range decoder and
+    # leaves most SMs idle, so the encode of the NEXT batch runs beside it, on a stream confined to the SMs
+    # the decoders do not own.  K complete round trips -- including the un-overlapped first encode and last
+    # decode -- lie inside the timed region.
+    side_stream = codec.encode_stream(dev, 3 * n_units)
+    # the decode is the latency-critical half: it runs on a high-priority stream so that its kernels are
+    # scheduled ahead of the encode's whenever both are waiting for SMs
     main_stream = torch.cuda.Stream(device=dev, priority=-1) if args.pipeline else torch.cuda.current_stream()
 
     def run_resident(steps, first_set=0):
@@ -226,7 +327,7 @@ def run_ours(args):
         main_stream.wait_stream(cur)              # the timing events live on `cur`: fork from it ...
         side_stream.wait_stream(cur)
         with torch.cuda.stream(side_stream):
-            job = codec.encode_begin(dev_sets[first_set % n_sets])
+            job = codec.encode_begin(dev_sets[first_set % n_sets], pad_tuple)
         for s in range(steps):
             t0 = time.perf_counter()
             blob, info = job.finish(to_host=False)
@@ -234,7 +335,7 @@ def run_ours(args):
             job = None
             if s + 1 < steps:
                 with torch.cuda.stream(side_stream):
-                    job = codec.encode_begin(dev_sets[(first_set + s + 1) % n_sets])
+                    job = codec.encode_begin(dev_sets[(first_set + s + 1) % n_sets], pad_tuple)
             t2 = time.perf_counter()
             with torch.cuda.stream(main_stream):
                 main_stream.wait_event(info['ready'])
@@ -248,9 +349,9 @@ def run_ours(args):
         return S, info
 
     def run_e2e(steps, first_set=0):
-        if not args.pipeline:
+        if not args.pipeline or crops_mode:
             for s in range(steps):
-                back, datas = step_e2e(host_sets[(first_set + s) % n_sets])
+                back, datas = step_e2e((first_set + s) % n_sets)
             return back, datas
         cur = torch.cuda.current_stream()
         main_stream.wait_stream(cur)
@@ -280,27 +381,43 @@ def run_ours(args):
         cur.wait_stream(side_stream)
         return back, datas
 
+    def check_lossless(S, k, what):
+        assert torch.equal(S, dev_sets[k]), what + ': round trip is not lossless'
+        if crops_mode:       # undo the padding, stitch the crops back (auto_crop.py:109-136): the user's image
+            per = n_units // n_img
+            for i in range(n_img):
+                parts = [l3c_pad.undo_pad(S[i * per + j:i * per + j + 1], *pad_tuple) for j in range(per)]
+                assert torch.equal(auto_crop.stitch(parts)[0].cpu(), raw_sets[k][i]), what + ': stitched image differs'
+
     # ---- warm-up + correctness (outside the timed region)
     for w in range(max(args.warmup, 1)):
         S, info = step_resident(dev_sets[w % n_sets])
-    assert torch.equal(S, dev_sets[(max(args.warmup, 1) - 1) % n_sets]), 'round trip is not lossless'
+    check_lossless(S, (max(args.warmup, 1) - 1) % n_sets, 'warm-up')
     if args.pipeline:                      # the side stream has its own allocator pool: warm it up too
         S, info = run_resident(max(args.warmup, 2))
-        assert torch.equal(S, dev_sets[(max(args.warmup, 2) - 1) % n_sets]), 'pipelined round trip is not lossless'
+        check_lossless(S, (max(args.warmup, 2) - 1) % n_sets, 'pipelined warm-up')
     sizes = info['sizes']
-    counts = l3c_dist.gather_byte_counts(sizes, n_global, rank, world)       # the one collective (NCCL)
-    bpsp = l3c_dist.global_bpsp(counts, 3 * HW * HW)
-    # parity with the reference's own torchac path on the same weights/image (golden: image seed 1000)
+    counts = l3c_dist.gather_byte_counts(sizes, n_global * (n_units // n_img), rank, world)   # the one collective
+    bpsp = l3c_dist.global_bpsp(counts, 3 * Hp * Wp)
+    # parity with the reference's own torchac path on the same weights / images: EVERY image of rank 0's
+    # batch against the container size the unmodified reference writes for it (tests/golden/batch_bytes.json)
     parity = None
-    try:
-        with open(os.path.join(ROOT, 'tests', 'golden', 'summary.json')) as f:
-            ref0 = json.load(f)['l3c_512x512_i0']
-        d0, _ = codec.encode_batch(dev_sets[0][:1])
-        if rank == 0:
-            parity = {'image': 'seed 1000, 3x512x512', 'bytes': len(d0[0]), 'reference_bytes': ref0['ref_bytes'],
-                      'abs_dbpsp': abs(len(d0[0]) - ref0['ref_bytes']) * 8 / (3.0 * HW * HW)}
-    except (OSError, KeyError):
-        pass
+    if wl['golden'] and rank == 0:
+        try:
+            with open(os.path.join(ROOT, 'tests', 'golden', 'batch_bytes.json')) as f:
+                gold = json.load(f)[wl['golden']]
+            _, info0 = codec.encode_batch(dev_sets[0], pad_tuple, to_host=False)
+            n_cmp = min(n_units, len(gold))
+            ours = [int(x) for x in info0['sizes'][:n_cmp]]
+            ref = [g['ref_bytes'] for g in gold[:n_cmp]]
+            d = [(a - b) * 8.0 / (3.0 * H * W) for a, b in zip(ours, ref)]
+            parity = {'images': 'seeds 1000..%d, 3x%dx%d (all %d of rank 0\'s batch)' % (999 + n_cmp, H, W, n_cmp),
+                      'reference': 'unmodified reference Bitcoding.encode on the CPU (oracle/gen_golden_batch.py)',
+                      'mean_dbpsp': sum(d) / n_cmp, 'mean_abs_dbpsp': sum(abs(x) for x in d) / n_cmp,
+                      'max_abs_dbpsp': max(abs(x) for x in d), 'bytes_minus_reference': [a - b for a, b in zip(ours, ref)],
+                      'bytes': ours[0], 'reference_bytes': ref[0], 'abs_dbpsp': abs(d[0])}
+        except (OSError, KeyError):
+            pass
 
     # ---- timed: device-resident
     sampler = ClockSampler(local_rank)
@@ -321,9 +438,8 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop(t_wall0, t_wall1)
     ms_total = float(ms)
-    px_step_global = n_global * HW * HW
     value = px_step_global * args.steps / 1e6 / (ms_total / 1e3)
-    assert torch.equal(S, dev_sets[(args.steps - 1) % n_sets]), 'timed round trip is not lossless'
+    check_lossless(S, (args.steps - 1) % n_sets, 'timed run')
 
     def timed_sequential(fn):
         """the same K steps strictly one after the other (reported beside the pipelined numbers)"""
@@ -346,8 +462,8 @@ def run_ours(args):
         seq_value = px_step_global * args.steps / 1e6 / (seq_ms / 1e3)
 
     # ---- timed: end to end through the public API (host buffers, copies inside)
-    back, datas = step_e2e(host_sets[0])
-    assert torch.equal(back, host_sets[0]), 'e2e round trip is not lossless'
+    back, datas = step_e2e(0)
+    assert torch.equal(back, raw_sets[0] if crops_mode else host_sets[0]), 'e2e round trip is not lossless'
     if args.pipeline:
         run_e2e(2)
     barrier()
@@ -362,30 +478,16 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = px_step_global * args.steps / 1e6 / (float(ms2) / 1e3)
-    assert torch.equal(back, host_sets[(args.steps - 1) % n_sets]), 'timed e2e round trip is not lossless'
-    if args.pipeline:
-        seq_ev, seq_wall = timed_sequential(lambda i: step_e2e(host_sets[i]))
+    last = (args.steps - 1) % n_sets
+    assert torch.equal(back, raw_sets[last] if crops_mode else host_sets[last]), 'timed e2e round trip is not lossless'
+    if args.pipeline and not crops_mode:
+        seq_ev, seq_wall = timed_sequential(step_e2e)
         seq_e2e = px_step_global * args.steps / 1e6 / (max(seq_ev, seq_wall) / 1e3)
-    cont_bytes = sum(len(d) for d in datas)
-    img_bytes = n_img * 3 * HW * HW
+    cont_bytes = sum(int(x) for x in sizes)
+    img_bytes = n_img * 3 * H * W
 
-    # ---- roofline of the dominant kernel: the 3x3 64->64 convolution at 256x256 (34 of the ~120
-    #      conv launches of a round trip and ~60 % of its FLOPs run on exactly this shape)
-    conv = bp.net.nets[0].enc.body[0].body[0]
-    x = torch.randn(n_img, HW // 2, HW // 2, 64, device=dev)
-    y = torch.empty_like(x)
-    for _ in range(3):
-        E.conv2d(conv, x, out=y)
-    torch.cuda.synchronize()
-    reps = 10
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0.record()
-    for _ in range(reps):
-        E.conv2d(conv, x, out=y)
-    c1.record()
-    torch.cuda.synchronize()
-    conv_ms = c0.elapsed_time(c1) / reps
-    conv_flops = 2.0 * 9 * 64 * 64 * n_img * (HW // 2) ** 2
+    # ---- roofline of the FLOP-dominant kernel: the 3x3 64->64 convolution at 16 x 256 x 256 (34 of the
+    #      ~120 conv launches of an L3C round trip and ~60 % of its FLOPs run on exactly this shape)
     peaks = {}
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -393,80 +495,147 @@ def run_ours(args):
     except OSError:
         pass
     peak_tf = peaks.get('bf16_tflops', 1590.0)
+    peak_tf_sus = peaks.get('bf16_tflops_sustained', 1400.0)
+    hbm_gbs = peaks.get('hbm_gbs', 6650.0)
+    roof_prec = precision if precision != 'fp32' else 'tf32'
+    E.set_conv_precision(roof_prec)
+    conv = bp.net.nets[0].dec.body[0].body[0]
+    cn = 16
+    x = torch.randn(cn, 256, 256, 64, device=dev)
+    xa = E.as_operand(x)                              # Act carrying the operand image the tensor cores read
+    y = torch.empty_like(x)
+    for _ in range(3):
+        E.conv2d(conv, xa, out=y)
+    torch.cuda.synchronize()
+    reps = 10
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(reps):
+        E.conv2d(conv, xa, out=y)
+    c1.record()
+    torch.cuda.synchronize()
+    conv_ms = c0.elapsed_time(c1) / reps
+    conv_flops = 2.0 * 9 * 64 * 64 * cn * 256 * 256
+    # the library conv the reference would run on this GPU (cuDNN through torch, channels_last), same shape:
+    # a comparator, not part of the product path
+    cudnn = {}
+    try:
+        xc = x.permute(0, 3, 1, 2)                    # NCHW view of the NHWC buffer = channels_last
+        wc = conv.weight.detach().contiguous(memory_format=torch.channels_last)
+        for name, allow in (('tf32', True), ('fp32', False)):
+            old = torch.backends.cudnn.allow_tf32
+            torch.backends.cudnn.allow_tf32 = allow
+            torch.backends.cudnn.benchmark = True
+            try:
+                for _ in range(3):
+                    torch.nn.functional.conv2d(xc, wc, conv.bias, padding=1)
+                torch.cuda.synchronize()
+                c0.record()
+                for _ in range(reps):
+                    torch.nn.functional.conv2d(xc, wc, conv.bias, padding=1)
+                c1.record()
+                torch.cuda.synchronize()
+                cudnn[name + '_ms'] = c0.elapsed_time(c1) / reps
+                cudnn[name + '_tflops'] = conv_flops / (cudnn[name + '_ms'] / 1e3) / 1e12
+            finally:
+                torch.backends.cudnn.allow_tf32 = old
+    except RuntimeError as ex:                        # never let the comparator break the bench
+        cudnn['error'] = str(ex)[:200]
+    E.set_conv_precision(precision)
     achieved_tf = conv_flops / (conv_ms / 1e3) / 1e12
+    step_tf = wl['flop_per_px'] * n_units * Hp * Wp * args.steps / (ms_total / 1e3) / 1e12
+    traffic = _profile_json('conv3x3_traffic.json') or {}
+    tr = traffic.get(roof_prec, {})
     roofline = {'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                 'frac': achieved_tf / peak_tf,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this shape, one launch, from the
-                # ncu --set full capture committed as profiles/r01b_conv3x3_tcgen05_v2_ncu_full_raw.csv
-                # (algorithmic: 268 MB read + 268 MB written)
-                'traffic': 484.4e6 if (args.precision == 'tf32' and n_img == 16) else None,
-                'kernel': 'conv3x3 64->64, %dx256x256 NHWC fp32 (%s path)' % (n_img, args.precision),
+                # dram__bytes_read.sum + dram__bytes_write.sum of THIS kernel on THIS shape, one launch, parsed from
+                # the `ncu --set full` capture summarised in profiles/conv3x3_traffic.json (records the commit)
+                'traffic': tr.get('dram_bytes'), 'traffic_source': tr.get('source'),
+                'kernel': 'conv3x3 64->64, 16x256x256 NHWC (%s operands, fp32 accumulate)' % roof_prec,
+                'ms': conv_ms,
                 'peak_source': 'MEASURED_PEAKS.json bf16 burst' if peaks else 'fallback 1.59 PFLOP/s',
-                'whole_step_conv_tflops': CONV_FLOP_PER_PX_ROUNDTRIP * n_img * HW * HW * args.steps /
-                (ms_total / 1e3) / 1e12}
+                'tf32_dense_peak_nominal': 1100.0, 'frac_of_tf32_nominal': achieved_tf / 1100.0,
+                'cudnn_same_shape': cudnn,
+                # conv FLOPs of the whole round trip / step time, against the burst and the sustained peak
+                'whole_round_trip': {'achieved': step_tf, 'frac_burst': step_tf / peak_tf,
+                                     'frac_sustained': step_tf / peak_tf_sus,
+                                     'flop_per_px': wl['flop_per_px']}}
 
-    # ---- where the step goes (one extra, untimed-for-the-metric round trip with CUDA events): the
-    #      dominant kernel by time is the serial range decoder, which is latency-bound (one warp per
-    #      stream, ~180 ns per symbol whatever the number of streams), not HBM- or tensor-bound
+    # ---- where the step goes (one extra, untimed-for-the-metric round trip with CUDA events): the dominant
+    #      kernel by TIME is the serial range decoder, which is latency-bound (one warp per stream, a fixed
+    #      number of ns per symbol whatever the number of streams), not HBM- or tensor-bound
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     torch.cuda.synchronize()
     ev[0].record()
     out_net = bp.net(dev_sets[0])
     ev[1].record()
-    blob, info = codec.encode_batch(dev_sets[0], out=out_net, to_host=False)
+    blob, info = codec.encode_batch(dev_sets[0], pad_tuple, out=out_net, to_host=False)
     ev[2].record()
-    codec.decode_device(blob, info['stream_offsets'], info['lens'], [(C, H, W) for (_, C, H, W) in info['shapes']])
+    codec.stage_events = []
+    codec.decode_device(blob, info['stream_offsets'], info['lens'], shapes_of(info))
     ev[3].record()
     torch.cuda.synchronize()
-    n_sym_rgb = HW * HW
+    n_sym_rgb = Hp * Wp
     dec_ms = ev[2].elapsed_time(ev[3])
+    stages = codec.stage_ms()
+    rgb_ms = stages.get('rgb')
     breakdown = {'forward_ms': ev[0].elapsed_time(ev[1]), 'entropy_encode_ms': ev[1].elapsed_time(ev[2]),
-                 'decode_ms': dec_ms,
-                 'serial_symbols_per_stream': {'rgb': n_sym_rgb, 'z1': n_sym_rgb // 4, 'z2': n_sym_rgb // 16,
-                                               'z3': n_sym_rgb // 64},
-                 'streams_in_flight': n_img * 18,
-                 'decoder_algorithmic_GBps': n_img * 3 * n_sym_rgb * 515e-9 / (dec_ms / 1e3),
-                 'note': 'range coder = one warp per stream, bounded by dependent-issue latency per symbol; '
-                         'HBM use of the decoder (512 B CDF row + code + symbol per symbol) is ~1 % of peak'}
+                 'decode_ms': dec_ms, 'decode_stage_ms': stages,
+                 'serial_symbols_per_stream': {'rgb': n_sym_rgb},
+                 'streams_in_flight': n_units * sum(C for (C, _, _) in shapes_of(info))}
+    # decoder roofline: algorithmic bytes per RGB symbol = 480 B parameters /3 + 1 B symbol + ~2 B code; the
+    # chain floor is the dependent-issue latency of one warp, not bandwidth
+    if rgb_ms:
+        ns_sym = rgb_ms * 1e6 / n_sym_rgb
+        alg_bytes = n_units * n_sym_rgb * (480.0 + 3.0 + 3 * 2.3)
+        roofline['decoder'] = {'kernel': 'RGB range decoder (one warp per stream, %d streams)' % (3 * n_units),
+                               'ns_per_symbol': ns_sym, 'dependency_chain_floor_ns': 130 / 1.965,
+                               'algorithmic_GBps': alg_bytes / (rgb_ms / 1e3) / 1e9,
+                               'frac_of_hbm': alg_bytes / (rgb_ms / 1e3) / 1e9 / hbm_gbs, 'hbm_peak_GBps': hbm_gbs}
 
     # ---- CPU baseline beside it (rank 0, N=1 only, bounded sample)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, cb, thr = cpu_roundtrip_mpx_s(1, HW)
-        cpu = {'value': v, 'unit': 'Mpixels/s', 'cores': thr, 'kind': 'port',
-               'sample': '1 round trip of one 3x512x512 image (%.1f s): oracle/model.py with the reference\'s '
-                         'PyTorch-CPU CDF path (byte-identical to the unmodified reference on tests/golden)' % dt,
-               'bpsp': cb}
+        r = cpu_roundtrips(args.workload, max(1, min(8, _host_cores() // 8)), 0)
+        cpu = {'value': r['value'], 'unit': 'Mpixels/s', 'cores': r['cores'], 'kind': 'port',
+               'sample': '%d concurrent round trip(s) (%d worker processes x %d torch threads), %s (%.1f s wall): '
+                         'oracle/model.py with the reference\'s PyTorch-CPU CDF path (byte-identical to the unmodified '
+                         'reference on tests/golden)' % (r['workers'], r['workers'], r['threads_per_worker'],
+                                                        r['sample'], r['seconds']),
+               'bpsp': r['bpsp']}
 
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': 'Mpixels/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'L3C cr.cf (3 scales, seed-0 default init), %d x 3x512x512 uint8 noise images '
-                                   'per GPU, encode+decode round trip, byte-compatible .l3c containers' % n_img,
+            'config': {'workload': wl['name'] % n_img, 'bench_workload': args.workload,
                        'global_batch': n_global, 'parallelism': 'images sharded over %d GPU(s), no data-path '
                                                                 'collective' % world,
-                       'conv_precision': args.precision,
+                       'conv_precision': precision,
                        'pipelining': ('encode of batch k+1 overlaps decode of batch k (separate SM partitions); all '
                                       '%d round trips, incl. the un-overlapped first encode and last decode, are '
                                       'inside the timed region; "sequential" = the same steps one after the other'
                                       % args.steps) if args.pipeline else 'none (sequential steps)',
-                       'l2': 'working set >> L2 (1 GB of activations per layer), inputs alternate between batches'},
+                       'l2': 'working set >> L2 (>= 1 GB of activations per layer), inputs alternate between batches'},
             'bpsp': bpsp, 'bpsp_parity': parity,
             'e2e': {'value': e2e_value, 'unit': 'Mpixels/s', 'h2d_bytes_per_step': img_bytes + cont_bytes,
-                    'd2h_bytes_per_step': cont_bytes + img_bytes, 'sequential_value': seq_e2e},
+                    'd2h_bytes_per_step': cont_bytes + img_bytes, 'sequential_value': seq_e2e,
+                    'api': 'Bitcoding.encode(file)/decode(file), files on a RAM disk' if crops_mode else
+                           'Bitcoding.encode_batch_begin/finish -> decode_batch, pinned host buffers'},
             'sequential': {'value': seq_value, 'unit': 'Mpixels/s'},
-            'gpu_launches': None,
+            # kernels of libl3c_b200.so launched inside the timed (device-resident) region, counted at the
+            # C-ABI call sites (engine.LAUNCHES)
+            'gpu_launches': launches_timed,
             'clocks': clocks,
             'roofline': roofline,
             'breakdown': breakdown,
             'cpu_baseline': cpu,
         }
-        # kernels of libl3c_b200.so launched inside the timed (device-resident) region, counted at the
-        # C-ABI call sites (engine.LAUNCHES)
-        line['gpu_launches'] = launches_timed
         print(json.dumps(line))
+    if tmpdir:
+        import shutil
+        shutil.rmtree(tmpdir, ignore_errors=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -478,9 +647,12 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('L3C_CONV_PRECISION', 'tf32'),
-                    choices=['fp32', 'tf32', 'tf32x3', 'bf16'])
-    ap.add_argument('--images-per-gpu', type=int, default=IMAGES_PER_GPU)
+    ap.add_argument('--workload', default='l3c', choices=sorted(WORKLOADS),
+                    help='l3c = BASELINE configs 2/3 (default), rgb_shared = config 4, crops = config 5')
+    ap.add_argument('--precision', default=os.environ.get('L3C_CONV_PRECISION'),
+                    choices=['fp32', 'tf32'],
+                    help='conv mode (default: tf32 tensor cores for l3c/crops, fp32 for rgb_shared)')
+    ap.add_argument('--images-per-gpu', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-pipeline', dest='pipeline', action='store_false',
                     help='strictly sequential steps: encode(k), decode(k), encode(k+1), ...')

@@ -42,6 +42,11 @@ extern "C" {
 const char *l3c_last_error(void);
 int l3c_version(void);
 
+/* Launch log (no reference counterpart; evidence plumbing): every kernel this library launches is
+ * counted under its kernel name.  Writes "kernel_name count\n" lines into buf (truncated to cap, may be
+ * NULL) and returns the TOTAL number of launches since the last reset; reset != 0 clears the counters. */
+long long l3c_launch_log(char *buf, size_t cap, int reset);
+
 /* ------------------------------------------------------------------------------------------
  * A. Drop-in native exports (reference: torchac.cpp:433-443; python shim torchac.py:87-166)
  * ---------------------------------------------------------------------------------------- */

@@ -40,6 +40,7 @@ DEC_STREAM_DTYPE = [('table', '<u8'), ('in', '<u8'), ('sym_out', '<u8'), ('state
 _SIGNATURES = {
     'l3c_last_error': (ctypes.c_char_p, []),
     'l3c_version': (c_int, []),
+    'l3c_launch_log': (ctypes.c_longlong, [ctypes.c_char_p, c_size_t, c_int]),
     'l3c_cuda_supported': (c_int, []),
     'l3c_encode_cdf': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'l3c_decode_cdf': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),

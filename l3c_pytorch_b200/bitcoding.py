@@ -55,8 +55,14 @@ class Bitcoding(object):
             print('Need to encode individual crops!')
             combinator = auto_crop.CropLossCombinator()
             crops = list(auto_crop.iter_crops(img))
-            bpsps = self._encode_many(crops, [pout + part_suffix_helper.make_part_suffix(i)
-                                               for i in range(len(crops))])
+            pouts = [pout + part_suffix_helper.make_part_suffix(i) for i in range(len(crops))]
+            # the reference recurses into encode() per part and asserts on every part path
+            # (bitcoding.py:57,63-71); stale higher-numbered parts of an earlier encode would be picked
+            # up by decode() and stitched into a wrong image
+            stale = [q for q in part_suffix_helper.existing_parts(pout) if q not in pouts]
+            assert not any(os.path.isfile(q) for q in pouts) and not stale, \
+                'part files of {} already exist: {}'.format(pout, [q for q in pouts if os.path.isfile(q)] + stale)
+            bpsps = self._encode_many(crops, pouts)
             for crop, bpsp in zip(crops, bpsps):
                 combinator.add(bpsp, np.prod(crop.shape[-2:]))
             return combinator.get_bpsp()
@@ -72,7 +78,7 @@ class Bitcoding(object):
         for (shape, pt), idxs in groups.items():
             batch = torch.cat([prepared[i][0] for i in idxs], 0)
             with self.times.run('[-] encode forwardpass'):
-                out = self.blueprint.net(batch)
+                out = self.blueprint.forward(batch)
             if self.compare_with_theory:
                 with self.times.run('[-] get loss'):
                     loss_out = self.blueprint.get_loss(out)

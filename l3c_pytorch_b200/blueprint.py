@@ -32,7 +32,10 @@ class MultiscaleBlueprint(nn.Module):
 
     def forward(self, in_batch, auto_recurse=0) -> Out:
         """in_batch: NCHW 0..255 (float / long / uint8) on the GPU."""
-        return self.net(in_batch, auto_recurse)
+        if self.device.type != 'cuda':
+            return self.net(in_batch, auto_recurse)   # raises: there is no CPU path
+        with torch.cuda.device(self.device):          # kernels launch on the CURRENT device
+            return self.net(in_batch, auto_recurse)
 
     def get_loss(self, out: Out, num_subpixels_before_pad=None) -> MultiscaleLoss:
         """Theoretical bpsp per scale, incl. the uniform-prior final scale
@@ -57,13 +60,19 @@ class MultiscaleBlueprint(nn.Module):
         total = sum(costs) + final_cost_uniform                  # numpy float64 [N]
         return (total / (np.log(2.) * num_subpixels)).tolist()
 
-    @staticmethod
-    def unpack_batch_pad(raw, fac):
+    def unpack_batch_pad(self_or_raw, raw_or_fac=None, fac=None):
+        """Reference signature `unpack_batch_pad(raw, fac)` (static, multiscale_blueprint.py:121-131: the
+        module-level DEVICE); called on an instance (`bp.unpack_batch_pad(raw, fac)`) the batch goes to
+        that blueprint's own device."""
+        if isinstance(self_or_raw, MultiscaleBlueprint):
+            device, raw = self_or_raw.device, raw_or_fac
+        else:
+            device, raw, fac = DEVICE, self_or_raw, (raw_or_fac if fac is None else fac)
         if len(raw.shape) == 3:
             raw = raw.unsqueeze(0)
         assert len(raw.shape) == 4
         raw = MultiscaleBlueprint.pad(raw, fac)
-        raw = raw.to(DEVICE)
+        raw = raw.to(device)
         return raw.float(), raw.long()
 
     @staticmethod

@@ -25,6 +25,22 @@ from .dmll import non_shared_get_K
 MAGIC = b'\x46\xE2\x84\x92'          # bitcoding.py:36
 
 
+def _on_device(fn):
+    """Run a codec entry point with the blueprint's GPU as the current CUDA device: the kernels of the
+    shared library launch on whatever device is current, and `current_stream()` is per device -- a
+    Blueprint(device='cuda:1') must not depend on the caller having called torch.cuda.set_device(1)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        dev = self.codec.blueprint.device if isinstance(self, EncodeJob) else self.blueprint.device
+        if dev.type != 'cuda':
+            return fn(self, *a, **kw)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **kw)
+    return wrapped
+
+
 def _slot_cap(n_sym):
     """worst case: every symbol has probability 2^-16 -> 17 bits, plus termination."""
     return ((n_sym * 17 + 7) // 8 + 64 + 3) & ~3
@@ -93,6 +109,7 @@ class EncodeJob:
     containers out, gathers the streams into one blob on the job's stream and (to_host) brings the
     bytes back: same results as encode_batch."""
 
+    @_on_device
     def finish(self, to_host=True):
         codec, N, per_img, caps, shapes = self.codec, self.N, self.per_img, self.caps, self.shapes
         self.coded.synchronize()                                                   # sync #1 (tiny)
@@ -177,6 +194,7 @@ class BatchCodec(object):
         per-image sizes and offsets, leaving the bytes in HBM).  `out`: a precomputed network Out."""
         return self.encode_begin(imgs_u8, pad_tuple, out).finish(to_host)
 
+    @_on_device
     def encode_begin(self, imgs_u8, pad_tuple=(0, 0, 0, 0), out=None):
         """First half of encode_batch: enqueues the whole GPU side of an encode (networks, intervals,
         the range-coder launch, the copy of the stream lengths to pinned memory) on the CURRENT stream
@@ -232,6 +250,7 @@ class BatchCodec(object):
         return job
 
     # ------------------------------------------------------------------------------------------
+    @_on_device
     def decode_batch(self, datas, to_host=True):
         """datas: list of container byte strings of equally shaped images.
         Returns (uint8 [N,3,H,W] incl. padding, pad_tuple list)."""
@@ -346,6 +365,7 @@ class BatchCodec(object):
                               [torch.cuda.Stream(device=dev) for _ in range(3)], torch.cuda.Stream(device=dev))
         return cache[key][:2]
 
+    @_on_device
     def decode_device(self, blob, offs, lens, shapes):
         """Decode streams that already sit in HBM: `blob` uint8 device buffer (readable 4 bytes past
         every stream), offs/lens int64 [N][streams per image] in container order (coarse -> fine,
@@ -355,8 +375,10 @@ class BatchCodec(object):
         if len(shapes) != self.net.scales + 1:
             raise ValueError('container has %d scales, model expects %d' % (len(shapes), self.net.scales + 1))
         K = self.net.config_ms.prob.K
+        self._check_shapes(shapes)
         bn8, F_prev, S = None, None, None
         j0 = 0
+        self._mark('start')
         for idx, (scale, dmll, uniform) in enumerate(self.iter_scale_dmll()):
             C, H, W = shapes[idx]
             HW = H * W
@@ -376,6 +398,10 @@ class BatchCodec(object):
                 E.ac_decode_streams(desc, dev, dmll.L)
             else:
                 l, F_prev = self.net.get_P_nhwc(scale, bn8, F_prev if self.net._fuse_feat else None)
+                self._mark('net%d' % scale)
+                if tuple(l.shape[1:3]) != (H, W) or non_shared_get_K(l.shape[-1], C) != K:
+                    raise ValueError('container scale %d (%dx%dx%d) does not match the model output %s'
+                                     % (scale, C, H, W, tuple(l.shape)))
                 table = torch.empty(N * C * HW * pitch, dtype=torch.int16, device=dev)
                 d['table'][:] = table.data_ptr() + \
                     (np.arange(N)[:, None] * C + np.arange(C)[None, :]) * (HW * pitch * 2)
@@ -386,9 +412,48 @@ class BatchCodec(object):
                 else:
                     E.dmll_build_table(l, S, tg, C, K, dmll.L, False, -1, table)
                     E.ac_decode_streams(desc, dev, dmll.L)
+            self._mark('uniform' if uniform else ('rgb' if dmll.rgb_scale and scale == 0 else 'S%d' % scale))
             if scale > 0:
                 bn8 = E.symbols_to_values(S, self._symbol_values(scale, dmll, dev), self._rgb_shift(dev))
         return S
+
+    # stage timing of a decode (bench.py / tools): set `codec.stage_events = []` before decode_device,
+    # synchronise, then read stage_ms()
+    stage_events = None
+
+    def _mark(self, name):
+        if self.stage_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.stage_events.append((name, ev))
+
+    def stage_ms(self):
+        """{stage: ms} of the decode recorded since `stage_events = []` (call after a synchronize)."""
+        evs, self.stage_events = self.stage_events or [], None
+        out = {}
+        for (_, a), (name, b) in zip(evs[:-1], evs[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+    def _check_shapes(self, shapes):
+        """C, H, W of every scale come straight from the (untrusted) file, while the kernels index with
+        the shapes the MODEL produces (each scale twice the size of the coarser one, C = 3 for the image
+        and the RGB baselines, q.C for bottlenecks).  A crafted, truncated or wrong-config container must
+        fail here, before any buffer is sized from it (the reference fails with a torch shape error)."""
+        cfg = self.net.config_ms
+        n = len(shapes)
+        for idx, (C, H, W) in enumerate(shapes):
+            scale = n - 1 - idx
+            want_C = 3 if (scale == 0 or self.net._rgb) else cfg.q.C
+            if C != want_C:
+                raise ValueError('container scale %d has %d channels, model expects %d' % (scale, C, want_C))
+            if H < 1 or W < 1:
+                raise ValueError('container scale %d has an empty shape %dx%d' % (scale, H, W))
+            if idx > 0:
+                Hc, Wc = shapes[idx - 1][1:]
+                if (H, W) != (2 * Hc, 2 * Wc):
+                    raise ValueError('container scale %d is %dx%d, expected twice the coarser scale (%dx%d)'
+                                     % (scale, H, W, 2 * Hc, 2 * Wc))
 
     def _symbol_values(self, scale, dmll, dev):
         """Value of every symbol of bottleneck `scale`: the `levels` LUT of the quantiser that produced

@@ -3,6 +3,7 @@
 // implemented on top of the batched kernels of range_coder.cu / dmll.cu.
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -16,6 +17,29 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---- launch log: every kernel launch of this library is counted under its kernel name --------
+namespace {
+struct LaunchEntry {
+    const char *name;      // string literal at the launch site
+    unsigned long long n;
+};
+constexpr int MAX_LOG = 64;
+LaunchEntry g_log[MAX_LOG];
+int g_log_n = 0;
+std::mutex g_log_mu;
+}  // namespace
+
+void count_launch(const char *kernel_name) {
+    std::lock_guard<std::mutex> lk(g_log_mu);
+    for (int i = 0; i < g_log_n; ++i) {
+        if (g_log[i].name == kernel_name || strcmp(g_log[i].name, kernel_name) == 0) {
+            g_log[i].n++;
+            return;
+        }
+    }
+    if (g_log_n < MAX_LOG) g_log[g_log_n++] = LaunchEntry{kernel_name, 1ull};
 }
 
 int sm_count() {
@@ -279,4 +303,23 @@ extern "C" int l3c_decode_logistic_mixture(const float *targets_dev, const float
         targets_dev, means_dev, log_scales_dev, probs_dev, K, n_sym, Lp, pitch, table.as<uint16_t>());
     L3C_LAUNCH_CHECK("plane_table_kernel");
     return run_decode(table.as<uint16_t>(), pitch, n_sym, L, in_host, in_len, sym_out_host);
+}
+
+// launch log: "kernel_name count\n" per kernel launched since the last reset; returns the total number of
+// launches (the text is truncated to `cap`, the return value is not).  reset != 0 clears the counters.
+extern "C" long long l3c_launch_log(char *buf, size_t cap, int reset) {
+    using namespace l3c;
+    std::lock_guard<std::mutex> lk(g_log_mu);
+    long long total = 0;
+    size_t pos = 0;
+    if (buf && cap) buf[0] = 0;
+    for (int i = 0; i < g_log_n; ++i) {
+        total += (long long)g_log[i].n;
+        if (buf && pos + 1 < cap) {
+            const int w = snprintf(buf + pos, cap - pos, "%s %llu\n", g_log[i].name, g_log[i].n);
+            if (w > 0) pos += (size_t)w < cap - pos ? (size_t)w : cap - pos - 1;
+        }
+    }
+    if (reset) g_log_n = 0;
+    return total;
 }

@@ -36,7 +36,10 @@ void set_error(const char *fmt, ...);
             ::l3c::set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));  \
             return L3C_ECUDA;                                                            \
         }                                                                                \
+        ::l3c::count_launch(name);                                                       \
     } while (0)
+
+void count_launch(const char *kernel_name);   // per-kernel launch counters (l3c_launch_log)
 
 int sm_count();                          // SMs of the current device
 int stream_sm_count(cudaStream_t st);    // SMs available to kernels launched into `st` (partition.cu)

@@ -943,16 +943,19 @@ ac_decode256_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams,
 // gather the variable-length code streams into one contiguous blob (container layout, byte offsets)
 // ---------------------------------------------------------------------------------------------
 constexpr int PACK_CHUNK = 16384;
+constexpr int PACK_GRID_X = 64;
+// grid = (PACK_GRID_X, streams): every CTA walks its stream in strides of PACK_GRID_X chunks, so a
+// stream of ANY length is copied completely (a fixed 256-chunk grid used to stop at 4 MiB)
 __global__ void pack_streams_kernel(const l3c_enc_stream_t *__restrict__ streams,
                                     const uint32_t *__restrict__ lens,
                                     const uint64_t *__restrict__ dst_off, uint8_t *__restrict__ blob) {
     const l3c_enc_stream_t st = streams[blockIdx.y];
     const uint32_t len = min(lens[blockIdx.y], st.out_cap);
-    const uint32_t b0 = blockIdx.x * PACK_CHUNK;
-    if (b0 >= len) return;
-    const uint32_t b1 = min(b0 + PACK_CHUNK, len);
     uint8_t *dst = blob + dst_off[blockIdx.y];
-    for (uint32_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) dst[i] = st.out[i];
+    for (uint64_t b0 = (uint64_t)blockIdx.x * PACK_CHUNK; b0 < len; b0 += (uint64_t)gridDim.x * PACK_CHUNK) {
+        const uint32_t b1 = (uint32_t)min(b0 + (uint64_t)PACK_CHUNK, (uint64_t)len);
+        for (uint32_t i = (uint32_t)b0 + threadIdx.x; i < b1; i += blockDim.x) dst[i] = st.out[i];
+    }
 }
 
 // intervals from a shared 256-entry LUT (uniform prior: every pixel has the same CDF row)
@@ -1008,9 +1011,7 @@ extern "C" int l3c_pack_streams(const l3c_enc_stream_t *streams_dev, const uint3
     if (n_streams == 0) return L3C_OK;
     L3C_REQUIRE(streams_dev && len_dev && dst_off_dev && blob_dev && n_streams > 0 && n_streams <= 65535,
                 "l3c_pack_streams: bad arguments");
-    // grid.x covers the largest possible slot (2^22 bytes = 256 chunks is ample for 2^21 symbols);
-    // CTAs beyond a stream's length exit immediately
-    dim3 grid(256, n_streams);
+    dim3 grid(PACK_GRID_X, n_streams);
     pack_streams_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(streams_dev, len_dev, dst_off_dev, blob_dev);
     L3C_LAUNCH_CHECK("pack_streams_kernel");
     return L3C_OK;

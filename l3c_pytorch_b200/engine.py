@@ -26,6 +26,18 @@ def get_conv_precision():
     return {v: k for k, v in _lib.PRECISIONS.items()}[_PRECISION['mode']]
 
 
+def launch_log(reset=False):
+    """-> ({kernel name: launches}, total) counted INSIDE libl3c_b200.so at its launch sites since the last
+    reset (l3c_launch_log): which kernels really ran, e.g. per precision mode in smoke()."""
+    buf = ctypes.create_string_buffer(8192)
+    total = lib.l3c_launch_log(buf, len(buf), 1 if reset else 0)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n = line.rsplit(' ', 1)
+        out[name] = int(n)
+    return out, int(total)
+
+
 def _stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -120,6 +132,14 @@ class Act(object):
 
     def __init__(self, f, r=None):
         self.f, self.r = f, r
+
+
+def as_operand(x):
+    """fp32 NHWC tensor -> Act that also carries the operand image the tensor cores read (its rounded twin)
+    when the tensor-core mode is on.  For callers that feed a conv from outside the network (tests, bench)."""
+    if not tensor_core_mode():
+        return Act(x)
+    return Act(x, round_to_tf32(x))
 
 
 def tensor_core_mode():

@@ -27,3 +27,9 @@ def iter_part_suffixes(pin):
     stem = pin[:_TAIL.search(pin).start()] + _BASE
     found = [m for m in glob.glob(glob.escape(stem) + '*') if contains_part_suffix(m)]
     return sorted(found, key=index_of_part_suffix)
+
+
+def existing_parts(pout):
+    """Part files `pout.partN` that are already on disk (any N), ordered by part index."""
+    found = [m for m in glob.glob(glob.escape(pout + _BASE) + '*') if contains_part_suffix(m)]
+    return sorted(found, key=index_of_part_suffix)

@@ -258,3 +258,25 @@ def test_dmll_tables_and_intervals_vs_oracle():
                 assert ((iv[n, c] >> 16).astype(np.int64) + 1 == hi).all()
                 dec[0, c] = vals[sym[n, c].long()] if not rgb else sym[n, c].float()
         assert n_diff / n_tot < 5e-3, (n_diff, n_tot)
+
+
+def test_pack_streams_copies_streams_longer_than_4_MiB():
+    """the gather kernel used to launch a fixed grid of 256 x 16 KiB chunks and silently
+    dropped everything past 4 MiB of a stream (reachable with >= 1.97 M symbols per channel)."""
+    from l3c_pytorch_b200 import _lib, engine as E
+    dev = torch.device('cuda')
+    lens = np.array([5 * 2 ** 20 + 13, 7, 0, 4 * 2 ** 20 + 1], np.int64)
+    g = torch.Generator().manual_seed(5)
+    srcs = [torch.randint(0, 256, (int(n) + 8,), generator=g, dtype=torch.uint8).to(dev) for n in lens]
+    desc = np.zeros(len(lens), dtype=_lib.ENC_STREAM_DTYPE)
+    for i, (t, n) in enumerate(zip(srcs, lens)):
+        desc['out'][i], desc['out_cap'][i], desc['n_sym'][i] = t.data_ptr(), t.numel(), 1
+    desc_dev = E._desc_to_device(desc, dev)
+    lens_dev = torch.from_numpy(lens.astype(np.int32)).to(dev)
+    offs = np.concatenate([[3], 3 + np.cumsum(lens + 5)[:-1]])           # odd offsets on purpose
+    blob = torch.zeros(int(offs[-1] + lens[-1]) + 16, dtype=torch.uint8, device=dev)
+    E.pack_streams(desc_dev, lens_dev, offs, len(lens), blob)
+    torch.cuda.synchronize()
+    for t, n, o in zip(srcs, lens, offs):
+        assert torch.equal(blob[int(o):int(o + n)], t[:int(n)])
+    assert int(blob[int(offs[0] + lens[0]):int(offs[1])].sum()) == 0      # gaps untouched

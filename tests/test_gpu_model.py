@@ -111,33 +111,71 @@ def test_goldens_of_the_reference(name, cfg, tmp_path, prec):
     # tf32 mode is only claimed at the 512^2 benchmark size, here it must merely stay close)
     slack = 2 + TOL[prec]['bytes_rel'] * summ['ref_bytes']
     assert abs(len(data) - summ['ref_bytes']) <= slack, (len(data), summ['ref_bytes'])
-    # cross-decode the reference's file
-    pr = str(tmp_path / 'ref.l3c')
-    open(pr, 'wb').write(ref)
+
+
+@pytest.mark.parametrize('name,cfg', [('l3c_32x32_i0', 'cr'), ('l3c_40x28_i1', 'cr'), ('rgbs_64x64_i0', 'cr_rgb_shared')])
+def test_cross_decode_of_reference_files(name, cfg, tmp_path):
+    """Decode the file the UNMODIFIED reference wrote (fp32 mode).  The uniform-prior scale is pure integer
+    arithmetic and MUST decode to the reference's symbols.  The DMLL scales need bit-identical CDF
+    integers at BOTH bounds of every coded symbol; CUDA expf/conv summation vs Sleef/MKL-DNN differ by one
+    count in < 0.5 % of the entries (test_dmll_tables_and_intervals_vs_oracle), and the first differing
+    bound desynchronises the coder for good -- the same holds between the reference's own CPU and GPU
+    backends.  So the full cross-decode is asserted where it holds and xfail-ed WITH the measured first
+    mismatch where it does not."""
+    from l3c_pytorch_b200 import Bitcoding, engine as E
+    g = util.golden_npz(name)
+    bp = util.blueprint(cfg)
+    bc = Bitcoding(bp)
+    img = torch.from_numpy(g['img'])
+    ref = g['container'].tobytes()
+    old = E.get_conv_precision()
+    E.set_conv_precision('fp32')
     try:
-        dec_r = bc.decode(pr)
-        cross_ok = torch.equal(dec_r[0].cpu(), img.long())
-    except Exception:
-        cross_ok = False
-    # cross-decoding needs bit-identical CDF integers on every coded symbol; report, and require it
-    # at least for the uniform-prior scale (pure integer path)
-    from l3c_pytorch_b200.codec import BatchCodec
-    print('cross-decode of reference file:', cross_ok, 'ours', len(data), 'ref', len(ref))
-    assert sc_o[0][3][0][1] == sc_r[0][3][0][1] or cfg != 'cr'
+        # uniform scale through the codec's own path: decode everything, then look at the coarsest symbols
+        from l3c_pytorch_b200.codec import parse_container
+        _, scales = parse_container(ref)
+        C, H, W, streams = scales[0]
+        L = 256 if cfg != 'cr' else 25
+        row = E.uniform_cdf_row(L)
+        from l3c_pytorch_b200 import torchac
+        cdf = torch.from_numpy(np.tile(row.view(np.int16), (1, H, W, 1)).copy())
+        key = 'S3' if cfg == 'cr' else 'S1'
+        for c, (off, n) in enumerate(streams):
+            sym = torchac.decode_cdf(cdf, ref[off:off + n])
+            assert torch.equal(sym.reshape(H, W).long(), torch.from_numpy(g[key][0, c].astype(np.int64))), c
+        pr = str(tmp_path / 'ref.l3c')
+        open(pr, 'wb').write(ref)
+        dec_r = bc.decode(pr)[0].cpu()
+    finally:
+        E.set_conv_precision(old)
+    if not torch.equal(dec_r, img.long()):
+        bad = (dec_r != img.long())
+        first = int(bad.flatten().nonzero()[0])
+        pytest.xfail('cross-decode of the reference file desynchronised: %d of %d sub-pixels differ, first at '
+                     'flat index %d (CDF integers differ by one count in <0.5%% of entries)'
+                     % (int(bad.sum()), bad.numel(), first))
 
 
 def test_round_trip_batch_512(prec):
-    """BASELINE config 2 shape (smaller batch): lossless + bpsp parity with the golden."""
+    """BASELINE config 2, the WHOLE batch (16 x 3x512x512, image seeds 1000..1015): lossless, and bpsp
+    of EVERY image within 1e-4 of what the unmodified reference writes for it (north-star tolerance;
+    goldens: tests/golden/batch_bytes.json, made by oracle/gen_golden_batch.py) -- mean and max."""
     from l3c_pytorch_b200 import Bitcoding
     bp = util.blueprint('cr')
     bc = Bitcoding(bp)
-    imgs = torch.stack([util.make_image(i, 512, 512) for i in range(2)])
+    imgs = torch.stack([util.make_image(i, 512, 512) for i in range(16)])
     datas, bpsps = bc.encode_batch(imgs)
     dec = bc.decode_batch(datas)
-    for i in range(2):
+    for i in range(16):
         assert torch.equal(dec[i][0].cpu(), imgs[i].long())
-    summ = util.golden_summary()['l3c_512x512_i0']
-    assert abs(bpsps[0] - summ['ref_bpsp']) < 1e-4, (bpsps[0], summ['ref_bpsp'], len(datas[0]), summ['ref_bytes'])
+    gold = util.golden_batch_bytes()['l3c_512x512']
+    assert [g['img_seed'] for g in gold] == list(range(1000, 1016))
+    d = util.bpsp_deltas([len(x) for x in datas], [g['ref_bytes'] for g in gold], 3 * 512 * 512)
+    print('512^2 batch parity [%s]: mean %+.2e, mean|.| %.2e, max|.| %.2e bpsp; bytes ours-ref %s'
+          % (prec, d.mean(), np.abs(d).mean(), np.abs(d).max(),
+             [len(x) - g['ref_bytes'] for x, g in zip(datas, gold)]))
+    assert np.abs(d).max() <= 1e-4, d
+    assert abs(bpsps[0] - gold[0]['ref_bpsp']) < 1e-4
     # batch-size independence of the bytes
     d1, _ = bc.encode_batch(imgs[:1])
     assert d1[0] == datas[0]
@@ -164,21 +202,31 @@ def test_crops_and_parts(tmp_path, monkeypatch):
 
 
 def test_rgb_shared_256(prec):
+    """BASELINE config 4, the whole batch (32 x 3x256x256, cr_rgb_shared.cf) against the unmodified
+    reference's container size of EVERY image.  One byte is 4.07e-5 bpsp here, and at random init nearly
+    every symbol sits on a 1- or 2-count CDF interval, where a last-bit difference in a parameter (other
+    summation order than MKL-DNN, CUDA vs Sleef expf) halves or doubles its probability: single images
+    scatter by a few bytes either way.  What must hold: no bias -- the batch MEAN within 1e-4 (fp32: the
+    strict mode of this config) -- and no image further than 4 bytes (1.6e-4) from the reference.  The
+    tf32 tensor-core mode is not claimed for this one-scale baseline (measured ~5e-4)."""
     from l3c_pytorch_b200 import Bitcoding
     bp = util.blueprint('cr_rgb_shared')
     bc = Bitcoding(bp)
-    imgs = torch.stack([util.make_image(i, 256, 256) for i in range(2)])
+    imgs = torch.stack([util.make_image(i, 256, 256) for i in range(32)])
     datas, bpsps = bc.encode_batch(imgs)
     dec = bc.decode_batch(datas)
-    for i in range(2):
+    for i in range(32):
         assert torch.equal(dec[i][0].cpu(), imgs[i].long())
-    summ = util.golden_summary()['rgbs_256x256_i0']
-    # one byte is 4e-5 bpsp at 256^2; the +-1-count differences between CUDA and glibc expf move the
-    # size by a few bytes either way, so allow 1e-4 plus two bytes.  The tf32 tensor-core mode is only
-    # claimed for the L3C 512^2 benchmark (test_round_trip_batch_512); for this one-scale baseline it
-    # lands at ~5e-4, so the RGB baselines should run with precision 'fp32'.
-    tol = 1e-4 + 2 * 8 / (3 * 256 * 256) if prec == 'fp32' else 2e-3
-    assert abs(bpsps[0] - summ['ref_bpsp']) < tol, (len(datas[0]), summ['ref_bytes'])
+    gold = util.golden_batch_bytes()['rgbs_256x256']
+    d = util.bpsp_deltas([len(x) for x in datas], [g['ref_bytes'] for g in gold], 3 * 256 * 256)
+    print('rgb-shared 256^2 batch parity [%s]: mean %+.2e, mean|.| %.2e, max|.| %.2e bpsp; bytes ours-ref %s'
+          % (prec, d.mean(), np.abs(d).mean(), np.abs(d).max(),
+             [len(x) - g['ref_bytes'] for x, g in zip(datas, gold)]))
+    if prec == 'fp32':
+        assert abs(d.mean()) <= 1e-4, d
+        assert np.abs(d).max() <= 4 * 8 / (3 * 256 * 256) + 1e-12, d
+    else:
+        assert abs(d.mean()) < 2e-3, d
 
 
 def test_corrupt_file_is_detected(tmp_path):
@@ -354,3 +402,53 @@ def test_sm_partition_streams_run_kernels_and_report_group_sizes():
             assert torch.equal(got, want)
     finally:
         E.set_conv_precision(old)
+
+
+def test_crafted_container_headers_raise_before_the_kernels_run():
+    """C/H/W come from the file; a wrong-config or crafted header must raise ValueError (the
+    reference fails with a torch shape error) -- never reach a kernel with buffers sized from the file."""
+    import struct
+    from l3c_pytorch_b200 import Bitcoding
+    from l3c_pytorch_b200.codec import parse_container
+    bp = util.blueprint('cr')
+    bc = Bitcoding(bp)
+    datas, _ = bc.encode_batch(util.make_image(3, 32, 32).unsqueeze(0))
+    good = datas[0]
+    _, scales = parse_container(good)
+    # header of the finest scale: u8 C, u16 H, u16 W sits 5 bytes before its first stream-length field
+    off_rgb = scales[3][3][0][0] - 4 - 5
+    assert struct.unpack_from('<BHH', good, off_rgb) == (3, 32, 32)
+    for patch in [(3, 16, 16), (3, 32, 64), (3, 64, 64)]:
+        bad = bytearray(good)
+        struct.pack_into('<BHH', bad, off_rgb, *patch)
+        with pytest.raises(ValueError):
+            bc.decode_batch([bytes(bad)])
+    off_z1 = scales[2][3][0][0] - 4 - 5
+    assert struct.unpack_from('<BHH', good, off_z1) == (5, 16, 16)
+    bad = bytearray(good)
+    struct.pack_into('<BHH', bad, off_z1, 5, 8, 8)
+    with pytest.raises(ValueError):
+        bc.decode_batch([bytes(bad)])
+    # a file of the RGB-shared model given to the L3C model: wrong number of scales
+    bcs = Bitcoding(util.blueprint('cr_rgb_shared'))
+    ds, _ = bcs.encode_batch(util.make_image(3, 32, 32).unsqueeze(0))
+    with pytest.raises(ValueError):
+        bc.decode_batch(ds)
+    with pytest.raises(ValueError):
+        bcs.decode_batch([good])
+    assert torch.equal(bc.decode_batch([good])[0][0].cpu(), util.make_image(3, 32, 32).long())
+
+
+def test_part_files_are_not_overwritten(tmp_path, monkeypatch):
+    from l3c_pytorch_b200 import Bitcoding
+    monkeypatch.setenv('AC_NEEDS_CROP_DIM', '40,40')
+    bc = Bitcoding(util.blueprint('cr'))
+    img = util.make_image(0, 100, 60)
+    p = str(tmp_path / 'crop.l3c')
+    bc.encode(img.long(), p)
+    with pytest.raises(AssertionError):
+        bc.encode(img.long(), p)                                      # part0..3 exist
+    q = str(tmp_path / 'other.l3c')
+    open(q + '.part7', 'wb').close()                                  # a stale higher-numbered part
+    with pytest.raises(AssertionError):
+        bc.encode(img.long(), q)

@@ -47,7 +47,13 @@ def test_harness_theory_and_write_to_files(tmp_path, capsys):
         one = tester.blueprint.get_loss(out, num_subpixels_before_pad=int(np.prod(raw.shape)))
         want = float(sum(one.nonrecursive_bpsps))
         assert abs(res.per_img[name] - want) <= 1e-5 * want, (name, res.per_img[name], want)
-    assert 17.0 < res.mean() < 24.0          # noise under default-init weights (c also pays for its padding)
+    # THEORETICAL cost of uint8 noise under default-init weights: ~39 bpsp (the reference itself reports
+    # 36.4 + 2.3 + 0.6 + 0.1 at 32^2, tests/golden/summary.json `ref_theory_bpsps`: the cross-entropy is
+    # not floored at 16 bits per symbol the way the 16-bit coder is); c also pays for its padding
+    # (48*40 coded sub-pixels counted against 44*36)
+    for name in ('a', 'b'):
+        assert 36.0 < res.per_img[name] < 43.0, (name, res.per_img[name])
+    assert 36.0 * (48 * 40) / (44 * 36) < res.per_img['c'] < 43.0 * (48 * 40) / (44 * 36), res.per_img['c']
 
     assert H.main([logs, '0306_0001', str(imgs), '--names', 'seed0']) == 0        # served from the cache
     out = capsys.readouterr().out
@@ -56,7 +62,12 @@ def test_harness_theory_and_write_to_files(tmp_path, capsys):
     out_dir, rep = str(tmp_path / 'l3c_out'), str(tmp_path / 'times.txt')
     assert H.main([logs, '0306_0001', str(imgs), '--write_to_files', out_dir, '--time_report', rep]) == 0
     assert sorted(os.listdir(out_dir)) == ['a.l3c', 'b.l3c', 'c.l3c']           # lossless: checked inside
+    # CODED size: every RGB symbol costs at most 16 bits + the three bottleneck scales at most
+    # log2(25) bits per symbol (5/4, 5/16, 5/64 symbols per pixel) + headers -> ~18.6 bpsp on the PADDED
+    # sub-pixels (what the reference measures, bitcoding.py:108-110); far BELOW the theoretical cost above
     for name in ('a', 'b', 'c'):
-        real = 8.0 * os.path.getsize(os.path.join(out_dir, name + '.l3c')) / (3 * (64 * 64 if name != 'c' else 44 * 36))
-        assert abs(real - res.per_img[name]) < 0.05 * res.per_img[name], (name, real, res.per_img[name])
+        padded = 3 * (64 * 64 if name != 'c' else 48 * 40)
+        real = 8.0 * os.path.getsize(os.path.join(out_dir, name + '.l3c')) / padded
+        assert 15.0 < real < 19.2, (name, real)
+        assert real < res.per_img[name]
     assert open(rep).read().startswith('Average times:')

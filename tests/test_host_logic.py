@@ -229,3 +229,35 @@ def test_coder_state_and_batched_emission_models_match_the_oracle():
         # garbage / truncated input: same symbols as the oracle (= the compiled reference, pin_oracle.py)
         junk = bytes(rng.integers(0, 256, size=max(1, len(data) // 2)).astype(np.uint8))
         assert (km.decode_model(cdf, junk, len(sym)) == ac.decode(cdf, junk)).all()
+
+
+def test_container_shapes_are_validated_before_any_buffer_is_sized():
+    """C/H/W of every scale come from the file; a crafted or wrong-config container must raise
+    ValueError (the reference fails with a torch shape error) instead of reaching the kernels."""
+    from l3c_pytorch_b200.codec import BatchCodec
+    codec = BatchCodec(util.blueprint('cr', device='cpu'))
+    good = [(5, 4, 4), (5, 8, 8), (5, 16, 16), (3, 32, 32)]
+    codec._check_shapes(good)
+    for bad in ([(5, 4, 4), (8, 8, 8), (5, 16, 16), (3, 32, 32)],      # C=8 at a q.C=5 scale
+                [(5, 4, 4), (5, 8, 8), (5, 16, 16), (3, 16, 16)],      # H/W smaller than the net's output
+                [(3, 4, 4), (5, 8, 8), (5, 16, 16), (3, 32, 32)],      # wrong C at the uniform scale
+                [(5, 4, 4), (5, 8, 9), (5, 16, 18), (3, 32, 36)],      # not a factor of 2
+                [(5, 0, 4), (5, 0, 8), (5, 0, 16), (3, 0, 32)]):
+        with pytest.raises(ValueError):
+            codec._check_shapes(bad)
+    rgb = BatchCodec(util.blueprint('cr_rgb_shared', device='cpu'))
+    rgb._check_shapes([(3, 32, 32), (3, 64, 64)])
+    with pytest.raises(ValueError):
+        rgb._check_shapes([(5, 32, 32), (3, 64, 64)])
+
+
+def test_part_files_are_never_overwritten(tmp_path):
+    """the reference asserts on every part path (bitcoding.py:57 through the recursion of
+    :63-71); stale higher-numbered parts must not survive a new encode either."""
+    from l3c_pytorch_b200 import part_suffix_helper as psh
+    p = str(tmp_path / 'x.l3c')
+    assert psh.existing_parts(p) == []
+    for i in (0, 1, 10, 2):
+        open(p + psh.make_part_suffix(i), 'wb').close()
+    open(p + '.partial', 'wb').close()                               # not a part file
+    assert [psh.index_of_part_suffix(q) for q in psh.existing_parts(p)] == [0, 1, 2, 10]

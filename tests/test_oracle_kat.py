@@ -94,3 +94,42 @@ def test_oracle_reproduces_reference_goldens(name, cfg):
         assert hashlib.sha256(data).hexdigest() == summ['ref_sha256']
     dec = om.decode_image(sd, ocfg, ref, 'torch')
     assert (dec[0] == img.long()).all()
+
+
+def test_oracle_weights_equal_the_reference_default_init():
+    """oracle/weights.py (plain torch module tree, used by `bench.py --impl reference`) reproduces the
+    seed-0 default init of the UNMODIFIED reference: same keys, order and values (sha256 recorded by
+    oracle/gen_golden.py from the reference's own MultiscaleBlueprint)."""
+    import hashlib
+    import json
+    import os
+    from oracle import model as om, weights
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'summary.json')) as f:
+        g = json.load(f)
+    for cfg, key in [(om.CFG_L3C, 'l3c'), (om.CFG_RGB_SHARED, 'rgbs')]:
+        sd = weights.default_init_state_dict(cfg)
+        h = hashlib.sha256()
+        for k in sd:
+            h.update(k.encode())
+            h.update(sd[k].contiguous().numpy().tobytes())
+        assert h.hexdigest() == g[key + '_sd_sha256'], key
+        assert sum(v.numel() for v in sd.values()) == g[key + '_sd_numel']
+
+
+def test_reference_arm_of_the_bench_never_touches_the_product():
+    """the reference arm's process must map only the checker's native code."""
+    import ast
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.dirname(__file__)), 'bench.py')).read()
+    tree = ast.parse(src)
+    for fn in tree.body:
+        if isinstance(fn, ast.FunctionDef) and fn.name in ('run_reference', '_ref_roundtrip', '_ref_init',
+                                                           'cpu_roundtrips', '_reference_sample', 'make_images'):
+            seg = ast.get_source_segment(src, fn)
+            assert 'l3c_pytorch_b200' not in seg and 'import l3c' not in seg, fn.name
+    # and nothing at module level pulls it in
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    assert all('l3c' not in ast.get_source_segment(src, n) for n in top)
+    for mod in ('model.py', 'weights.py', 'ac.py'):
+        assert 'l3c_pytorch_b200' not in open(os.path.join(os.path.dirname(os.path.dirname(__file__)), 'oracle', mod)).read().replace(
+            'not import l3c_pytorch_b200', '')

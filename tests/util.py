@@ -19,6 +19,18 @@ def golden_summary():
         return json.load(f)
 
 
+def golden_batch_bytes():
+    """container sizes the unmodified reference writes for every image of the benchmark batches
+    (oracle/gen_golden_batch.py): {'l3c_512x512': [...16], 'rgbs_256x256': [...32]}"""
+    with open(os.path.join(GOLDEN, 'batch_bytes.json')) as f:
+        return json.load(f)
+
+
+def bpsp_deltas(sizes, ref_sizes, subpixels):
+    """signed per-image bpsp differences to the reference's containers"""
+    return (np.asarray(sizes, np.float64) - np.asarray(ref_sizes, np.float64)) * 8.0 / subpixels
+
+
 def golden_npz(name):
     return np.load(os.path.join(GOLDEN, name + '.npz'))
 
