@@ -174,21 +174,27 @@ int l3c_dmll_channel_params(const float *l_dev, const float *x_dec_dev, int N, i
 
 #define L3C_CONV_RELU 1u            /* y = max(y, 0) after bias                                  */
 #define L3C_CONV_PIXEL_SHUFFLE2 2u  /* out[n,2h+i,2w+j,c] = y[n,h,w,4c+2i+j] (edsr.py:92-101)     */
-#define L3C_CONV_ROUND_TF32 4u      /* round y itself to TF32 (cvt.rna): y only feeds tensor-core convs */
+#define L3C_CONV_ROUND_TF32 4u      /* (TF32 mode) round y itself to TF32 (cvt.rna): y only feeds tensor-core convs */
 
 #define L3C_PREC_FP32 0             /* CUDA-core FFMA, fp32 throughout (bit-faithful ordering)    */
 #define L3C_PREC_TF32 1             /* tcgen05 kind::tf32 on operands pre-rounded to TF32 (RN), fp32 accumulate in TMEM */
-#define L3C_PREC_TF32X3 2           /* tcgen05, error-compensated 3xTF32 split (~fp32 accuracy)   */
-#define L3C_PREC_BF16 3             /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate         */
+#define L3C_PREC_F16 2              /* tcgen05 kind::f16 on FP16 operand images (RN, saturating; the same 10 mantissa */
+                                    /* bits as TF32-RN), fp32 accumulate in TMEM, fp32 residual stream               */
 
 typedef struct {
-    const float *x;        /* dev NHWC [N][H][W][x_pitch], channels [0,Cin) read                  */
-    const float *w;        /* dev [KH][KW][Cin][cout_pad]                                          */
+    const float *x;        /* dev NHWC [N][H][W][x_pitch] fp32, channels [0,Cin) read (FP32 / TF32 kernels)     */
+    const float *w;        /* dev [KH][KW][Cin][cout_pad] (FP32) or the TF32 operand image (TF32)                */
     const float *bias;     /* dev [cout_pad]                                                       */
     const float *residual; /* dev NHWC like the output (same pitch/offset), or NULL: y += res      */
-    float *y;              /* dev NHWC [N][Ho][Wo][y_pitch], channels [y_coff, y_coff+Cout) written */
+    float *y;              /* dev NHWC [N][Ho][Wo][y_pitch], channels [y_coff, y_coff+Cout) written; may be NULL  */
+                           /* in F16 mode when only y_h is wanted                                                */
     float *y_tf32;         /* optional second output, same layout as y: the result rounded to TF32     */
-                           /* (round-to-nearest) = operand image for a following tensor-core conv; NULL ok */
+                           /* (round-to-nearest) = operand image for a following TF32 tensor-core conv; NULL ok */
+    void *y_h;             /* optional output, same element pitch/offset as y: the result as FP16 (RN, saturating) */
+                           /* = operand image for a following F16 tensor-core conv; written by every kernel; NULL ok */
+    const void *x_h;       /* F16 tensor-core kernels: FP16 operand image of the input, NHWC [N][H][W][x_pitch]    */
+    const void *w_h;       /* F16 tensor-core kernels: FP16 weight image, 3x3: [9 taps][cout_pad][64],             */
+                           /* 1x1: [Cin/64][cout_pad][64]                                                         */
     int N, H, W, Cin, x_pitch;
     int Cout, cout_pad, y_pitch, y_coff;
     int ksize, stride, dilation;   /* padding = ksize/2 if dilation==1 else dilation               */

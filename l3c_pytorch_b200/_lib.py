@@ -18,7 +18,7 @@ c_void_p, c_int, c_int64, c_size_t, c_uint32, c_float = (
 class ConvDesc(ctypes.Structure):
     """l3c_conv_t"""
     _fields_ = [('x', c_void_p), ('w', c_void_p), ('bias', c_void_p), ('residual', c_void_p),
-                ('y', c_void_p), ('y_tf32', c_void_p),
+                ('y', c_void_p), ('y_tf32', c_void_p), ('y_h', c_void_p), ('x_h', c_void_p), ('w_h', c_void_p),
                 ('N', c_int), ('H', c_int), ('W', c_int), ('Cin', c_int), ('x_pitch', c_int),
                 ('Cout', c_int), ('cout_pad', c_int), ('y_pitch', c_int), ('y_coff', c_int),
                 ('ksize', c_int), ('stride', c_int), ('dilation', c_int),
@@ -28,9 +28,9 @@ class ConvDesc(ctypes.Structure):
 CONV_RELU = 1
 CONV_PIXEL_SHUFFLE2 = 2
 CONV_ROUND_TF32 = 4
-PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_BF16 = 0, 1, 2, 3
+PREC_FP32, PREC_TF32, PREC_F16 = 0, 1, 2
 E_UNSUPPORTED = -5          # L3C_EUNSUPPORTED
-PRECISIONS = {'fp32': PREC_FP32, 'tf32': PREC_TF32, 'tf32x3': PREC_TF32X3, 'bf16': PREC_BF16}
+PRECISIONS = {'fp32': PREC_FP32, 'tf32': PREC_TF32, 'f16': PREC_F16}
 
 # numpy dtypes of the stream descriptor structs (l3c_enc_stream_t / l3c_dec_stream_t)
 ENC_STREAM_DTYPE = [('intervals', '<u8'), ('out', '<u8'), ('n_sym', '<u4'), ('out_cap', '<u4')]

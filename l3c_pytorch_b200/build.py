@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(HERE, 'libl3c_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-SOURCES = ['capi.cu', 'range_coder.cu', 'dmll.cu', 'conv_ffma.cu', 'conv_tcgen05.cu', 'bicubic.cu', 'partition.cu']
+SOURCES = ['capi.cu', 'range_coder.cu', 'dmll.cu', 'conv_ffma.cu', 'conv_tcgen05.cu', 'conv_f16.cu', 'bicubic.cu', 'partition.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--fmad=true',
               '-DL3C_BUILDING_DSO']
@@ -37,7 +37,7 @@ def build(verbose=False, force=False):
         obj = os.path.join(build_dir, src.replace('.cu', '.o'))
         objs.append(obj)
         srcp = os.path.join(CSRC, src)
-        deps = [srcp, os.path.join(CSRC, 'common.cuh'),
+        deps = [srcp, os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'tc_ptx.cuh'),
                 os.path.join(os.path.dirname(HERE), 'include', 'l3c_b200.h')]
         if not force and os.path.isfile(obj) and os.path.getmtime(obj) >= max(map(os.path.getmtime, deps)):
             continue

@@ -41,6 +41,25 @@ def _on_device(fn):
     return wrapped
 
 
+def _under_injection_tool():
+    """True when a CUDA injection tool (Nsight Compute / Systems) is attached to this process: either it
+    announced itself through the environment or its injection libraries are mapped.  Nsight Compute cannot
+    profile kernels launched into green-context streams (it loses the process at the first one:
+    "Failed to prepare kernel for profiling"), so the SM partitions are switched off under it -- same
+    kernels, same bytes, ordinary streams; L3C_SM_PARTITION=1 forces them on."""
+    if any(k in os.environ for k in ('CUDA_INJECTION64_PATH', 'CUDA_INJECTION32_PATH', 'NVTX_INJECTION64_PATH')):
+        return True
+    try:
+        with open('/proc/self/maps') as f:
+            for line in f:
+                low = line.lower()
+                if 'nsight' in low or 'injection' in low:
+                    return True
+    except OSError:
+        pass
+    return False
+
+
 def _slot_cap(n_sym):
     """worst case: every symbol has probability 2^-16 -> 17 bits, plus termination."""
     return ((n_sym * 17 + 7) // 8 + 64 + 3) & ~3
@@ -345,7 +364,7 @@ class BatchCodec(object):
         if key not in cache:
             part = None
             want_part = os.environ.get('L3C_SM_PARTITION', '1') != '0'
-            if want_part and os.environ.get('CUDA_INJECTION64_PATH') and 'L3C_SM_PARTITION' not in os.environ:
+            if want_part and _under_injection_tool() and 'L3C_SM_PARTITION' not in os.environ:
                 # Nsight Compute cannot profile kernels launched into green-context streams (it lost the
                 # process at the first one): under a CUDA injection tool use ordinary streams
                 import sys

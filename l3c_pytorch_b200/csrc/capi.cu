@@ -56,6 +56,7 @@ int sm_count() {
 
 int conv2d_ffma(const l3c_conv_t &p, cudaStream_t st);
 int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st);
+int conv2d_f16(const l3c_conv_t &p, cudaStream_t st);
 
 // ---- helper kernels for the single-stream (reference-shaped) API -----------------------------
 
@@ -216,7 +217,12 @@ extern "C" int l3c_cuda_supported(void) {
 }
 
 extern "C" int l3c_conv2d(const l3c_conv_t *p, void *stream) {
-    L3C_REQUIRE(p && p->x && p->w && p->bias && p->y, "l3c_conv2d: null pointer");
+    L3C_REQUIRE(p && p->bias, "l3c_conv2d: null pointer");
+    if (p->precision == L3C_PREC_F16) {
+        L3C_REQUIRE(p->x_h && p->w_h && (p->y || p->y_h), "l3c_conv2d: F16 mode needs x_h, w_h and y or y_h");
+    } else {
+        L3C_REQUIRE(p->x && p->w && p->y, "l3c_conv2d: null pointer");
+    }
     L3C_REQUIRE(p->N >= 1 && p->N <= 65535 && p->H >= 1 && p->W >= 1, "l3c_conv2d: N=%d H=%d W=%d", p->N, p->H, p->W);
     L3C_REQUIRE(p->Cin >= 1 && p->x_pitch >= p->Cin && p->x_pitch % 4 == 0,
                 "l3c_conv2d: Cin=%d x_pitch=%d (pitch must be a multiple of 4)", p->Cin, p->x_pitch);
@@ -229,6 +235,7 @@ extern "C" int l3c_conv2d(const l3c_conv_t *p, void *stream) {
         L3C_REQUIRE(p->y_pitch >= p->y_coff + p->Cout, "l3c_conv2d: y_pitch=%d y_coff=%d Cout=%d", p->y_pitch, p->y_coff, p->Cout);
     }
     if (p->precision == L3C_PREC_FP32) return conv2d_ffma(*p, (cudaStream_t)stream);
+    if (p->precision == L3C_PREC_F16) return conv2d_f16(*p, (cudaStream_t)stream);
     return conv2d_tcgen05(*p, (cudaStream_t)stream);
 }
 

@@ -15,6 +15,8 @@
 //                                                                  multiscale_network.py:181-183
 //   to_q 1x1 + Quantizer (eval) ................................... modules/net.py:116-148,
 //                                                                  modules/quantizer.py:62-90
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace l3c {
@@ -37,6 +39,15 @@ __device__ __forceinline__ float round_tf32(float x) {      // round-to-nearest 
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
+}
+// two floats -> packed fp16 pair (round-to-nearest-even, saturating): the F16 operand image (conv_f16.cu)
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ void store_h(void *base, size_t idx, float v) {
+    reinterpret_cast<uint16_t *>(base)[idx] = (uint16_t)(pack_h2(v, 0.f) & 0xFFFFu);
 }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
@@ -179,6 +190,13 @@ conv_ffma_kernel(l3c_conv_t p, int Ho, int Wo, int tiles_x, int pad) {
                     *reinterpret_cast<float4 *>(p.y_tf32 + off + 4) =
                         make_float4(round_tf32(v[4]), round_tf32(v[5]), round_tf32(v[6]), round_tf32(v[7]));
                 }
+                if (p.y_h && ((p.y_pitch | p.y_coff) & 7) == 0) {
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(p.y_h) + off) =
+                        make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+                } else if (p.y_h) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) store_h(p.y_h, off + c, v[c]);
+                }
                 if (round_y) {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) v[c] = round_tf32(v[c]);
@@ -192,6 +210,7 @@ conv_ffma_kernel(l3c_conv_t p, int Ho, int Wo, int tiles_x, int pad) {
                         float o = v[c];
                         if (p.residual) o += __ldg(p.residual + off + c);
                         if (p.y_tf32) p.y_tf32[off + c] = round_tf32(o);
+                        if (p.y_h) store_h(p.y_h, off + c, o);
                         p.y[off + c] = round_y ? round_tf32(o) : o;
                     }
                 }
@@ -209,6 +228,7 @@ conv_ffma_kernel(l3c_conv_t p, int Ho, int Wo, int tiles_x, int pad) {
                 float o = v[c];
                 if (p.residual) o += __ldg(p.residual + off);
                 if (p.y_tf32) p.y_tf32[off] = round_tf32(o);
+                if (p.y_h) store_h(p.y_h, off, o);
                 p.y[off] = round_y ? round_tf32(o) : o;
             }
         }

@@ -23,10 +23,11 @@
 // pre-rounded to TF32 with round-to-nearest: weights once on the host side, activations by the
 // producing layer's epilogue, which writes a second, rounded copy (`y_tf32`) next to the fp32 tensor
 // that residual adds and the fp32 layers keep using.  Accumulation is fp32 in TMEM.
-// (3xTF32 / bf16 are not built yet: the dispatcher says so loudly.)
+// (The faster FP16-operand variant of this path is conv_f16.cu, precision L3C_PREC_F16.)
 #include <cuda.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace l3c {
 
@@ -42,53 +43,8 @@ constexpr int ACC_COLS = 64;
 constexpr int TMEM_COLS = 128;                 // two accumulators
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
-// ---- PTX wrappers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
-                                            int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// ---- PTX wrappers shared with conv_f16.cu: tc_ptx.cuh
+using namespace tcx;
 
 // D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -99,10 +55,6 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
-}
-// arrive on an mbarrier once all previously issued MMAs of this thread have completed
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     uint32_t r[16];
@@ -116,32 +68,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-
-// tcgen05.ld shape 16x256b, 4 column repeats: 16 TMEM lanes x 32 columns per instruction.  Register
-// layout (the mma C-fragment layout): thread t holds, for column block j = 0..3,
-//   r[4j+0], r[4j+1] = (lane t/4    , columns 8j + 2*(t%4) + {0,1})
-//   r[4j+2], r[4j+3] = (lane t/4 + 8, same columns)
-// so the four threads of a quad own 32 contiguous bytes of one row: full-sector global stores.
-__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float *v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFFu)      // start address
-           | (1ull << 16)                              // leading byte offset (16 B, unused for SW128 K-major)
-           | (64ull << 32)                             // stride byte offset: 1024 B between 8-row groups
-           | (1ull << 46)                              // descriptor version (Blackwell)
-           | (2ull << 61);                             // SWIZZLE_128B
-}
 
 // instruction descriptor: D=f32, A=B=tf32, both K-major, N=64, M=128
 constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
@@ -498,21 +424,18 @@ conv3x3_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
         const uint32_t tfull0 = bar_base + 8u * (8 * k + 4), tempty0 = bar_base + 8u * (8 * k + 6);
         uint32_t stage = 0, phase = 0;
         uint32_t acc = 0, acc_phase = 0;
-        if (lane == 0) mbar_wait(wbar, 0);
-        __syncwarp();
+        mbar_wait(wbar, 0);
         for (int t = blockIdx.x + k * gridDim.x; t < ptiles; t += V2_PIPES * gridDim.x) {
-            if (lane == 0) {
-                mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);
-                tc_fence_after();
-            }
-            __syncwarp();
+            // warp-uniform code, MMAs issued through elect.sync: descriptors stay in uniform registers
+            mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);
+            tc_fence_after();
             const uint32_t d_tmem = tmem_base + (k * 2 + acc) * ACC_COLS;
             for (int unit = 0; unit < 6; ++unit) {
-                if (lane == 0) {
-                    mbar_wait(full0 + 8u * stage, phase);
-                    tc_fence_after();
-                    const int dx = unit >> 1, kh = unit & 1;
-                    const uint32_t a0 = a_base + stage * a_bytes;
+                mbar_wait(full0 + 8u * stage, phase);
+                tc_fence_after();
+                const int dx = unit >> 1, kh = unit & 1;
+                const uint32_t a0 = a_base + stage * a_bytes;
+                if (elect_one()) {
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
                         const uint64_t da = make_desc(a0 + dy * d * (TW * 128));           // dy*d rows of 16 px
@@ -614,12 +537,10 @@ conv3x3_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
     }
 }
 
-// ---- host side ------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+}  // namespace tc
 
-static EncodeTiledFn get_encode_fn() {
+namespace tcx {
+EncodeTiledFn get_encode_fn() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void *p = nullptr;
@@ -630,13 +551,12 @@ static EncodeTiledFn get_encode_fn() {
     }
     return fn;
 }
-
-}  // namespace tc
+}  // namespace tcx
 
 int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st) {
     using namespace tc;
     if (p.precision != L3C_PREC_TF32) {
-        set_error("l3c_conv2d: precision mode %d is not built (available: fp32, tf32)", p.precision);
+        set_error("l3c_conv2d: precision mode %d is not built (available: fp32, tf32, f16)", p.precision);
         return L3C_EINVAL;
     }
     // The tensor-core kernel covers the 3x3 / 64-input-channel layers (> 92 % of the FLOPs of a round

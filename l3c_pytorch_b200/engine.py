@@ -12,13 +12,14 @@ import torch
 from . import _lib
 from ._lib import lib, check, ConvDesc
 
-# default conv precision: env L3C_CONV_PRECISION (fp32 | tf32); see set_conv_precision
+# default conv precision: env L3C_CONV_PRECISION (fp32 | tf32 | f16); see set_conv_precision
 LAUNCHES = {'n': 0}        # kernels of libl3c_b200.so launched through this module (bench.py reports it)
 _PRECISION = {'mode': _lib.PRECISIONS[os.environ.get('L3C_CONV_PRECISION', 'fp32')]}
 
 
 def set_conv_precision(name):
-    """'fp32' (CUDA-core FFMA, bit-faithful), 'tf32x3', 'tf32', 'bf16' (tcgen05 tensor cores)."""
+    """'fp32' (CUDA-core FFMA, bit-faithful ordering), 'tf32' (tcgen05 kind::tf32 on TF32-RN operands),
+    'f16' (tcgen05 kind::f16 on FP16-RN operand images: same 10 mantissa bits, half the bytes and MMAs)."""
     _PRECISION['mode'] = _lib.PRECISIONS[name]
 
 
@@ -101,6 +102,7 @@ class PackedConv(object):
             bp[:cout] = b.detach().float()
             self.w, self.b, self._key = wp, bp, key
             self.w_tc = None
+            self.w_h = None
         return self.w, self.b
 
     def get_tc(self):
@@ -118,6 +120,29 @@ class PackedConv(object):
         return self.w_tc, b
 
 
+def _get_f16(self):
+    """F16 tensor-core operand image (conv_f16.cu): 3x3 -> [9 taps][cout_pad][64 cin] fp16, 1x1 ->
+    [Cin/64][cout_pad][64] fp16; K-major rows of 128 B; values rounded to FP16 (RN, saturating)."""
+    _, b = self.get()
+    if getattr(self, 'w_h', None) is None:
+        w = self.conv.weight.detach().float().clamp(-65504.0, 65504.0)
+        cout, cin, kh, kw = w.shape
+        cout_pad = (cout + 63) // 64 * 64
+        assert cin % 64 == 0 and kh == kw and kh in (1, 3)
+        if kh == 3:
+            assert cin == 64
+            img = torch.zeros(9, cout_pad, 64, dtype=torch.float16, device=w.device)
+            img[:, :cout] = w.permute(2, 3, 0, 1).reshape(9, cout, 64).half()
+        else:
+            img = torch.zeros(cin // 64, cout_pad, 64, dtype=torch.float16, device=w.device)
+            img[:, :cout] = w.reshape(cout, cin // 64, 64).permute(1, 0, 2).half()
+        self.w_h = img.contiguous()
+    return self.w_h, b
+
+
+PackedConv.get_f16 = _get_f16
+
+
 def round_to_tf32(t):
     """fp32 tensor -> nearest TF32-representable fp32 (10-bit mantissa, ties away from zero like
     `cvt.rna.tf32.f32`).  Host-side preparation of the tensor-core weight image."""
@@ -126,8 +151,10 @@ def round_to_tf32(t):
 
 
 class Act(object):
-    """An activation tensor (NHWC fp32) plus, in tensor-core mode, its TF32-rounded twin that the
-    next tcgen05 conv consumes (see conv_tcgen05.cu).  `r is f` when the tensor itself is rounded."""
+    """An activation: `f` = NHWC fp32 tensor, `r` = the operand image the next tensor-core conv reads --
+    in tf32 mode an fp32 tensor rounded to TF32 (`r is f` when the tensor itself is rounded), in f16 mode
+    an FP16 tensor of the same shape (conv_f16.cu); then `f` is None for activations that feed nothing but
+    tensor-core convs (want='round')."""
     __slots__ = ('f', 'r')
 
     def __init__(self, f, r=None):
@@ -139,11 +166,17 @@ def as_operand(x):
     when the tensor-core mode is on.  For callers that feed a conv from outside the network (tests, bench)."""
     if not tensor_core_mode():
         return Act(x)
+    if f16_mode():
+        return Act(x, x.clamp(-65504.0, 65504.0).half())
     return Act(x, round_to_tf32(x))
 
 
 def tensor_core_mode():
     return _PRECISION['mode'] != _lib.PREC_FP32
+
+
+def f16_mode():
+    return _PRECISION['mode'] == _lib.PREC_F16
 
 
 def _packed_obj(conv):
@@ -182,9 +215,12 @@ def conv2d(conv, x, cin=None, relu=False, residual=None, pixel_shuffle=False, ou
     (used for the atrous concat, prob_clf.py:71).
 
     x: tensor or Act.  want: 'plain' -> tensor; 'act' -> Act whose `.r` twin is produced when the
-    tensor-core mode is on; 'round' -> Act whose only tensor is TF32-rounded (for activations that
-    feed nothing but a following tensor-core conv)."""
+    tensor-core mode is on; 'round' -> Act whose only tensor is the operand image (for activations that
+    feed nothing but a following tensor-core conv; then `out`, if given, is that image's buffer)."""
     xa = x if isinstance(x, Act) else Act(x)
+    mode = _PRECISION['mode'] if precision is None else precision
+    if mode == _lib.PREC_F16:
+        return _conv2d_f16(conv, xa, cin, relu, residual, pixel_shuffle, out, out_coff, want)
     x = xa.f
     require_cuda(x, 'x')
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
@@ -202,7 +238,6 @@ def conv2d(conv, x, cin=None, relu=False, residual=None, pixel_shuffle=False, ou
             out = torch.empty(N, Ho * 2, Wo * 2, cout // 4, dtype=torch.float32, device=x.device)
         else:
             out = torch.empty(N, Ho, Wo, cout, dtype=torch.float32, device=x.device)
-    mode = _PRECISION['mode'] if precision is None else precision
     prec = mode
     x_in = x
     if mode != _lib.PREC_FP32 and tc_eligible(conv, xp, out.shape[-1], out_coff, pixel_shuffle) and cin == conv.in_channels:
@@ -233,6 +268,78 @@ def conv2d(conv, x, cin=None, relu=False, residual=None, pixel_shuffle=False, ou
     if want == 'round':
         return Act(out, out if mode != _lib.PREC_FP32 else None)
     return Act(out, out_r)
+
+
+def _conv2d_f16(conv, xa, cin, relu, residual, pixel_shuffle, out, out_coff, want):
+    """conv2d in precision mode 'f16': tensor-core-eligible layers read the FP16 operand image `xa.r` and
+    run conv_f16.cu; the others (5x5/s2, Cin = 3 or 5) run the fp32 FFMA kernel on `xa.f`.  Either kernel
+    writes what the consumers need: fp32 (`want` 'plain' / 'act') and / or the FP16 image ('act' / 'round')."""
+    src = xa.f if xa.f is not None else xa.r
+    require_cuda(src, 'x')
+    assert src.is_contiguous() and src.dim() == 4
+    N, H, W, xp = src.shape
+    kh = conv.kernel_size[0]
+    stride, dil = conv.stride[0], conv.dilation[0]
+    cin = conv.in_channels if cin is None else cin
+    cout = conv.out_channels
+    pad = kh // 2 if dil == 1 else dil
+    Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    flags = (_lib.CONV_RELU if relu else 0) | (_lib.CONV_PIXEL_SHUFFLE2 if pixel_shuffle else 0)
+    shape = (N, Ho * 2, Wo * 2, cout // 4) if pixel_shuffle else (N, Ho, Wo, cout)
+    need_f, need_h = want in ('plain', 'act'), want in ('act', 'round')
+    y = y_h = None
+    if out is not None:                      # caller's buffer for the primary output (channel slice)
+        if want == 'round':
+            assert out.dtype == torch.float16
+            y_h = out
+        else:
+            assert out.dtype == torch.float32
+            y = out
+    k = kh
+    tc = (stride == 1 and xp == conv.in_channels and cin == conv.in_channels and
+          ((k == 3 and cin == 64 and cout % 64 == 0) or
+           (k == 1 and cin % 64 == 0 and not pixel_shuffle and cout % 2 == 0 and cout <= 256 and residual is None)))
+    if need_f and y is None:
+        y = torch.empty(shape, dtype=torch.float32, device=src.device)
+    if need_h and y_h is None:
+        y_h = torch.empty(shape, dtype=torch.float16, device=src.device)
+    ref = y if y is not None else y_h
+    pc = _packed_obj(conv)
+    if tc:
+        if xa.r is None or xa.r.dtype != torch.float16:
+            xa = as_operand(xa.f)                     # callers from outside the network (tests, bench)
+        w_h, b = pc.get_f16()
+        d = ConvDesc(x_h=xa.r.data_ptr(), w_h=w_h.data_ptr(), bias=b.data_ptr(),
+                     residual=residual.data_ptr() if residual is not None else None,
+                     y=_dp(y), y_h=_dp(y_h), N=N, H=H, W=W, Cin=cin, x_pitch=xp, Cout=cout, cout_pad=b.shape[0],
+                     y_pitch=ref.shape[-1], y_coff=out_coff, ksize=kh, stride=stride, dilation=dil,
+                     flags=flags, precision=_lib.PREC_F16)
+    else:
+        assert xa.f is not None, 'an fp32 (CUDA-core) layer needs the fp32 activation'
+        if y is None:                                 # the FFMA kernel always writes fp32
+            y = torch.empty(shape, dtype=torch.float32, device=src.device)
+        w, b = pc.get()
+        d = ConvDesc(x=xa.f.data_ptr(), w=w.data_ptr(), bias=b.data_ptr(),
+                     residual=residual.data_ptr() if residual is not None else None,
+                     y=_dp(y), y_h=_dp(y_h), N=N, H=H, W=W, Cin=cin, x_pitch=xp, Cout=cout, cout_pad=b.shape[0],
+                     y_pitch=ref.shape[-1], y_coff=out_coff, ksize=kh, stride=stride, dilation=dil,
+                     flags=flags, precision=_lib.PREC_FP32)
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.shape == ref.shape and residual.is_contiguous()
+    if y is not None and y_h is not None:
+        assert y.shape == y_h.shape
+    check(lib.l3c_conv2d(ctypes.byref(d), _stream_ptr()))
+    LAUNCHES['n'] += 1
+    if want == 'plain':
+        return y
+    if want == 'round':
+        return Act(None, y_h)
+    return Act(y, y_h)
+
+
+def _dp(t):
+    return t.data_ptr() if t is not None else None
 
 
 def rgb_prep(img_u8, conv1, conv2):

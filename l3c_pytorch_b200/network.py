@@ -101,8 +101,8 @@ class Upsampler(nn.Sequential):
         assert scale == 2
         super(Upsampler, self).__init__(conv(n_feats, 4 * n_feats, 3, True), nn.PixelShuffle(2))
 
-    def forward(self, x):
-        return E.conv2d(self[0], x, pixel_shuffle=True, want='act')
+    def forward(self, x, want='act'):
+        return E.conv2d(self[0], x, pixel_shuffle=True, want=want)
 
 
 class Head(nn.Module):
@@ -201,12 +201,14 @@ class EDSRDec(nn.Module):
         self.body = nn.Sequential(*m_body)
         self.tail = Upsampler(conv, 2, Cf)
 
-    def forward(self, bn8, features_to_fuse=None):
-        """bn8: NHWC [N,h,w,8] (q.C channels used); features_to_fuse: engine.Act or tensor or None."""
+    def forward(self, bn8, features_to_fuse=None, operand_only=False):
+        """bn8: NHWC [N,h,w,8] (q.C channels used); features_to_fuse: engine.Act or tensor or None.
+        operand_only: the features feed nothing but the probability classifier's tensor-core convs (finest
+        scale) -> in f16 mode only their FP16 operand image is written."""
         fuse = features_to_fuse.f if isinstance(features_to_fuse, E.Act) else features_to_fuse
         x = E.conv2d(self.head, bn8, residual=fuse, want='act')       # head(x) + F_prev
         x = _run_body(self.body, x)
-        return DecOut(self.tail(x))                                   # engine.Act
+        return DecOut(self.tail(x, 'round' if (operand_only and E.f16_mode()) else 'act'))   # engine.Act
 
 
 class Net(nn.Module):
@@ -231,13 +233,16 @@ class StackedAtrousConvs(nn.Module):
 
     def forward(self, x):
         """x: engine.Act -> NHWC parameter tensor."""
-        N, H, W, Cin = x.f.shape
-        cat = torch.empty(N, H, W, Cin * len(self.atrous), dtype=torch.float32, device=x.f.device)
+        src = x.f if x.f is not None else x.r
+        N, H, W, Cin = src.shape
+        # f16 mode: the concat buffer IS the FP16 operand image of the 1x1 conv
+        cat = torch.empty(N, H, W, Cin * len(self.atrous), device=src.device,
+                          dtype=torch.float16 if E.f16_mode() else torch.float32)
         for i, a in enumerate(self.atrous):
             # concat by channel slice; `cat` only feeds the 1x1 conv -> TF32-rounded in place when the
             # tensor cores are on
             E.conv2d(a, x, out=cat, out_coff=i * Cin, want='round')
-        return E.conv2d(self.lin, cat)
+        return E.conv2d(self.lin, E.Act(None, cat) if E.f16_mode() else cat)
 
 
 class AtrousProbabilityClassifier(nn.Module):
@@ -394,21 +399,22 @@ class MultiscaleNetwork(nn.Module):
         prev = None
         for s in reversed(range(self.scales)):
             fuse = prev if (self._fuse_feat and s != self.scales - 1) else None
-            prev = self.nets[s].dec(enc_outs[s].bn_q, fuse).F
+            prev = self.nets[s].dec(enc_outs[s].bn_q, fuse, operand_only=(s == 0)).F
             dec_F[s] = prev
         for s in range(self.scales):
             out.append(enc_outs[s], self.prob_clfs[s](dec_F[s]))
         return out
 
-    def get_P_nhwc(self, scale, bn8, dec_F_prev=None):
-        """-> (parameters NHWC, decoder features as engine.Act for the next finer scale)."""
+    def get_P_nhwc(self, scale, bn8, dec_F_prev=None, need_F=False):
+        """-> (parameters NHWC, decoder features as engine.Act for the next finer scale).  At scale 0 the
+        features feed nothing else (need_F=True keeps their fp32 tensor for the reference-shaped get_P)."""
         assert 0 <= scale < self.config_ms.num_scales, 'Out of range: {}'.format(scale)
-        F = self.nets[scale].dec(bn8, dec_F_prev).F
+        F = self.nets[scale].dec(bn8, dec_F_prev, operand_only=(scale == 0 and not need_F)).F
         return self.prob_clfs[scale](F), F
 
     def get_P(self, scale, bn_q, dec_F_prev=None):
         """multiscale_network.py:308-322 with NCHW-shaped tensors in and out."""
         bn8 = to_nhwc(bn_q, 8)
         Fp = None if dec_F_prev is None else to_nhwc(dec_F_prev)
-        l, F = self.get_P_nhwc(scale, bn8, Fp)
+        l, F = self.get_P_nhwc(scale, bn8, Fp, need_F=True)
         return nchw_view(l), nchw_view(F.f)

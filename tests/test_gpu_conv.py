@@ -176,3 +176,101 @@ def test_tcgen05_1x1_conv(cin, cout, H, W):
     got = E.conv2d(conv.cuda(), _nhwc(x), precision=_lib.PREC_TF32)
     assert got.shape == (2, H, W, cout)
     np.testing.assert_allclose(got.cpu().permute(0, 3, 1, 2).numpy(), want.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def _h(x):
+    """fp32 -> the FP16 operand image's value (RN, saturating), as fp32"""
+    return x.clamp(-65504.0, 65504.0).half().float()
+
+
+@pytest.mark.parametrize('cout,rate,H,W,kw', [(64, 1, 16, 16, {}), (64, 2, 24, 40, {}), (64, 4, 19, 37, {}),
+                                              (256, 1, 12, 20, dict(pixel_shuffle=True)), (64, 1, 8, 16, dict(relu=True)),
+                                              (64, 1, 3, 5, {}), (64, 1, 40, 72, dict(residual=True)),
+                                              (128, 1, 17, 33, dict(relu=True)), (64, 4, 64, 48, dict(residual=True))])
+def test_f16_conv_vs_torch_on_fp16_operands(cout, rate, H, W, kw):
+    """conv_f16.cu (TMA + tcgen05.mma kind::f16 + TMEM) against a PyTorch fp32 CPU conv fed with the SAME
+    FP16-rounded operands: products are exact in fp32, only the accumulation order differs -> rtol 1e-4.
+    Also: the three output modes ('plain' fp32, 'act' fp32 + FP16 image, 'round' FP16 image only) agree
+    bit for bit, the image is the RN-FP16 of the fp32 result, and nothing is written outside the tensor."""
+    from l3c_pytorch_b200 import engine as E, _lib
+    kw = dict(kw)
+    conv = _conv_module(64, cout, 3, 1, rate)
+    x = torch.randn(3, 64, H, W)
+    x[0, :, 0, 0] = 1e-6                                           # below the FP16 normal range
+    want = F.conv2d(_h(x), _h(conv.weight.detach()), conv.bias.detach(), padding=rate, dilation=rate)
+    res = None
+    if kw.pop('residual', False):
+        r = torch.randn(3, cout, H, W)
+        want = want + r
+        res = _nhwc(r)
+    if kw.get('relu'):
+        want = F.relu(want)
+    if kw.get('pixel_shuffle'):
+        want = F.pixel_shuffle(want, 2)
+    xa = E.as_operand(_nhwc(x)) if E.f16_mode() else E.Act(_nhwc(x), _nhwc(x).clamp(-65504.0, 65504.0).half())
+    cc = conv.cuda()
+    got = E.conv2d(cc, xa, precision=_lib.PREC_F16, want='act', residual=res, **kw)
+    np.testing.assert_allclose(got.f.cpu().permute(0, 3, 1, 2).numpy(), want.numpy(), rtol=1e-4, atol=1e-4)
+    assert got.r.dtype == torch.float16 and got.r.shape == got.f.shape
+    assert torch.equal(got.r.cpu(), got.f.cpu().clamp(-65504.0, 65504.0).half())
+    plain = E.conv2d(cc, xa, precision=_lib.PREC_F16, want='plain', residual=res, **kw)
+    assert torch.equal(plain, got.f)
+    r_only = E.conv2d(cc, xa, precision=_lib.PREC_F16, want='round', residual=res, **kw)
+    assert r_only.f is None and torch.equal(r_only.r, got.r)
+    if not kw.get('pixel_shuffle'):
+        # channel-slice output into a wider FP16 buffer (the atrous concat): neighbours untouched
+        buf = torch.full((3, H, W, 3 * cout), 7.0, dtype=torch.float16, device='cuda')
+        E.conv2d(cc, xa, precision=_lib.PREC_F16, want='round', residual=res, out=buf, out_coff=cout, **kw)
+        assert torch.equal(buf[..., cout:2 * cout], got.r)
+        assert bool((buf[..., :cout] == 7).all()) and bool((buf[..., 2 * cout:] == 7).all())
+
+
+@pytest.mark.parametrize('cin,cout,H,W', [(192, 120, 9, 31), (192, 150, 16, 16), (64, 64, 8, 16), (192, 120, 64, 64),
+                                          (128, 256, 5, 7)])
+def test_f16_1x1_conv(cin, cout, H, W):
+    """1x1 convs with Cin % 64 == 0 (the 192 -> Kp head) as one GEMM tile of 128 pixels x all output
+    channels; pixel counts that are not multiples of 128 and Cout that is not a multiple of 64."""
+    from l3c_pytorch_b200 import engine as E, _lib
+    conv = _conv_module(cin, cout, 1)
+    x = torch.randn(2, cin, H, W)
+    want = F.conv2d(_h(x), _h(conv.weight.detach()), conv.bias.detach())
+    xa = E.Act(None, _nhwc(x).half())
+    got = E.conv2d(conv.cuda(), xa, precision=_lib.PREC_F16)
+    assert got.shape == (2, H, W, cout) and got.dtype == torch.float32
+    np.testing.assert_allclose(got.cpu().permute(0, 3, 1, 2).numpy(), want.numpy(), rtol=1e-4, atol=1e-4)
+    both = E.conv2d(conv.cuda(), xa, precision=_lib.PREC_F16, want='act', relu=True)
+    np.testing.assert_allclose(both.f.cpu().permute(0, 3, 1, 2).numpy(), F.relu(want).numpy(), rtol=1e-4, atol=1e-4)
+    assert torch.equal(both.r.cpu(), both.f.cpu().half())
+
+
+def test_f16_conv_independent_of_batch_and_position():
+    """enc/dec bit-exactness of the f16 path: a pixel's result does not depend on the batch size, on which
+    image of the batch it is in, or on which tile / pipe / CTA computed it."""
+    from l3c_pytorch_b200 import engine as E, _lib
+    conv = _conv_module(64, 64, 3).cuda()
+    x = torch.randn(5, 64, 40, 56)
+    xa = E.Act(None, _nhwc(x).half())
+    full = E.conv2d(conv, xa, precision=_lib.PREC_F16)
+    one = E.conv2d(conv, E.Act(None, xa.r[3:4].contiguous()), precision=_lib.PREC_F16)
+    assert torch.equal(full[3:4], one)
+    # same content placed elsewhere in a larger image: interior results (2 px away from the seam) identical
+    big = torch.zeros(1, 80, 112, 64, dtype=torch.float16, device='cuda')
+    big[0, 24:64, 40:96] = xa.r[3]
+    moved = E.conv2d(conv, E.Act(None, big), precision=_lib.PREC_F16)
+    assert torch.equal(moved[0, 25:63, 41:95], full[3, 1:39, 1:55])
+
+
+def test_ffma_writes_the_f16_image():
+    """CUDA-core layers (5x5/s2 down conv, Cin = 3 or 5) also produce the FP16 operand image in f16 mode."""
+    from l3c_pytorch_b200 import engine as E, _lib
+    conv = _conv_module(64, 64, 5, stride=2).cuda()
+    x = _nhwc(torch.randn(2, 64, 20, 36))
+    old = E.get_conv_precision()
+    E.set_conv_precision('f16')
+    try:
+        got = E.conv2d(conv, x, want='act')
+    finally:
+        E.set_conv_precision(old)
+    want = E.conv2d(conv, x, precision=FP32)
+    assert torch.equal(got.f, want)
+    assert torch.equal(got.r, want.clamp(-65504.0, 65504.0).half())
