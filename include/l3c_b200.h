@@ -167,6 +167,13 @@ int l3c_dmll_channel_params(const float *l_dev, const float *x_dec_dev, int N, i
                             int rgb, int c, float *pi_dev, float *mu_dev, float *log_scales_dev,
                             void *stream);
 
+/* Sample every sub-pixel from its mixture (logistic_mixture.py:277-323; used by test.py --sample): Gumbel-max
+ * choice of the component from u_sel_dev f32 [N][C][K][HW], inverse-CDF sample of its logistic from u_x_dev f32
+ * [N][C][HW] (both uniform in [1e-5, 1 - 1e-5], supplied by the caller), RGB: means coupled through the
+ * coefficients of the chosen components and values clamped to [0, 255].  x_dev f32 [N][C][HW] out. */
+int l3c_dmll_sample(const float *l_dev, const float *u_sel_dev, const float *u_x_dev, int N, int HW, int C, int K,
+                    int rgb, float *x_dev, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * D. Convolution stack (reference: modules/net.py:89-184, edsr.py:52-119, head.py:26-59,
  *    prob_clf.py:29-74, pytorch_ext.py:57-61; all nn.Conv2d fp32)
@@ -234,8 +241,8 @@ int l3c_bicubic_half_u8(const uint8_t *in_dev, int N, int H, int W, uint8_t *out
 
 /* Streams confined to two disjoint groups of SMs of the current device (driver green contexts):
  * `n_a` streams (high priority) whose kernels only run on a group of about `sm_a` SMs (the driver
- * rounds up to its granularity, 8 on sm_90+), `n_b` streams on the remaining SMs (the first three of
- * them high priority, further ones default priority).  Used by the
+ * rounds up to its granularity, 8 on sm_90+), `n_b` streams on the remaining SMs (all but the last of
+ * them high priority, the last one default priority).  Used by the
  * pipelined RGB decode (reference: the strictly serial R -> G -> B loop of bitcoding.py:199-237) so
  * that the latency-bound decoder warps do not share SMs with the CDF-row builders.  The streams
  * belong to the primary context (same memory, events interoperate) and live until process exit;

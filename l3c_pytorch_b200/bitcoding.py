@@ -134,11 +134,17 @@ class Bitcoding(object):
             job = self.codec.encode_begin(x, pt)
         return _BatchEncodeJob(job, int(np.prod(x.shape[1:])))
 
-    def side_stream(self, n_images):
-        """Stream for encode_batch_begin() calls that should overlap a decode_batch of `n_images`."""
-        return self.codec.encode_stream(self._device(), 3 * n_images)
+    def side_stream(self, n_images, n_lanes=1):
+        """Stream for encode_batch_begin() calls that should overlap decode_batch calls of `n_images` each."""
+        return self.codec.encode_stream(self._device(), 3 * n_images, n_lanes)
 
-    def decode_batch(self, datas):
+    def decode_lanes(self, n_images, n_lanes=2):
+        """Stream sets for `n_lanes` decode_batch calls in flight at the same time (codec.BatchCodec.lanes):
+        `with torch.cuda.stream(lane.main): dec = bc.decode_batch(datas, lane=lane)` returns at once; the
+        decode of one batch is bound by the serial chain of its range coder and leaves most of the GPU idle."""
+        return self.codec.lanes(self._device(), 3 * n_images, n_lanes)[0]
+
+    def decode_batch(self, datas, lane=None):
         """list of container bytes (any mix of shapes) -> list of int64 1CHW tensors (GPU)."""
         from .codec import parse_container
         keys = {}
@@ -147,7 +153,7 @@ class Bitcoding(object):
             keys.setdefault((pt, tuple((C, H, W) for (C, H, W, _) in scales)), []).append(i)
         outs = [None] * len(datas)
         for (pt, _), idxs in keys.items():
-            S, _ = self.codec.decode_batch([datas[i] for i in idxs], to_host=False)
+            S, _ = self.codec.decode_batch([datas[i] for i in idxs], to_host=False, lane=lane)
             for k, i in enumerate(idxs):
                 img = S[k:k + 1].long()
                 if any(pt):

@@ -47,7 +47,16 @@ class MultiscaleBlueprint(nn.Module):
         conversion = np.log(2.) * num_subpixels
         costs_bpsp = [cost / conversion for cost in costs]
         nonrecursive_bpsps = costs_bpsp[:out.auto_recursive_from] + [final_cost_uniform / conversion]
-        return MultiscaleLoss(sum(costs_bpsp), nonrecursive_bpsps, None)
+        recursive_bpsps = None
+        if out.auto_recursive_from is not None:
+            # non-recursive AND recursive scales, plus the uniform-prior cost of the very last scale
+            recursive_bpsps = costs_bpsp + [out.get_nat_count(-1) / conversion]
+        return MultiscaleLoss(sum(costs_bpsp), nonrecursive_bpsps, recursive_bpsps)
+
+    def sample_forward(self, in_batch, sample_scales, partial_final=None):
+        """multiscale_blueprint.py:97-98"""
+        with torch.cuda.device(self.device):
+            return self.net.sample_forward(in_batch, self.losses, sample_scales, partial_final)
 
     def get_loss_per_image(self, out: Out, num_subpixels_before_pad=None):
         """Total theoretical bpsp (all scales + the uniform-prior final scale) of every image of the
@@ -57,6 +66,8 @@ class MultiscaleBlueprint(nn.Module):
         if num_subpixels_before_pad:
             assert num_subpixels_before_pad <= num_subpixels, num_subpixels_before_pad
             num_subpixels = num_subpixels_before_pad
+        if out.auto_recursive_from is not None:                  # sum(recursive_bpsps): the last scale is the uniform one
+            final_cost_uniform = out.get_nat_count(-1) / out.S_u8[0].shape[0]
         total = sum(costs) + final_cost_uniform                  # numpy float64 [N]
         return (total / (np.log(2.) * num_subpixels)).tolist()
 

@@ -123,6 +123,11 @@ def parse_container(data):
     return pad_tuple, scales
 
 
+class DecodeLane(object):
+    """Streams of one decode in flight (BatchCodec.lanes)."""
+    __slots__ = ('main', 'dec', 'bld', 'partitioned')
+
+
 class EncodeJob:
     """An encode in flight (BatchCodec.encode_begin).  finish() waits for the stream lengths, lays the
     containers out, gathers the streams into one blob on the job's stream and (to_host) brings the
@@ -270,7 +275,7 @@ class BatchCodec(object):
 
     # ------------------------------------------------------------------------------------------
     @_on_device
-    def decode_batch(self, datas, to_host=True):
+    def decode_batch(self, datas, to_host=True, lane=None):
         """datas: list of container byte strings of equally shaped images.
         Returns (uint8 [N,3,H,W] incl. padding, pad_tuple list)."""
         dev = self.blueprint.device
@@ -294,13 +299,13 @@ class BatchCodec(object):
         offs = np.array([[starts[n] + o for (_, _, _, st) in parsed[n][1] for (o, _) in st] for n in range(N)],
                         np.int64)
         lens = np.array([[ln for (_, _, _, st) in parsed[n][1] for (_, ln) in st] for n in range(N)], np.int64)
-        S = self.decode_device(blob, offs, lens, ref_shapes)
+        S = self.decode_device(blob, offs, lens, ref_shapes, lane=lane)
         pads = [p[0] for p in parsed]
         if to_host:
             return S.cpu(), pads
         return S, pads
 
-    def _decode_rgb_pipelined(self, l, S, tg, C, K, L, table, d, dev, n_chunks=64):
+    def _decode_rgb_pipelined(self, l, S, tg, C, K, L, table, d, dev, n_chunks=64, lane=None):
         """RGB scale: channel c's means depend on the decoded channels < c at the same pixel
         (logistic_mixture.py:262-272), so the reference codes R, G, B strictly one after the other.
         Here the three serial decoders run concurrently, staggered by one chunk of pixels: as soon as
@@ -316,7 +321,9 @@ class BatchCodec(object):
         d['state'][:] = state.data_ptr() + 16 * (np.arange(N)[:, None] * C + np.arange(C)[None, :])
         descs = [E._desc_to_device(np.ascontiguousarray(d[:, c]), dev) for c in range(C)]
         cur = torch.cuda.current_stream()
-        s_bld, s_dec = self._rgb_streams(dev, N * C)
+        if lane is None:
+            lane = self.lanes(dev, N * C, 1)[0][0]
+        s_bld, s_dec = lane.bld, lane.dec
         start = torch.cuda.Event()
         start.record(cur)
         for st in s_bld[:C] + s_dec[:C]:
@@ -348,19 +355,24 @@ class BatchCodec(object):
             cur.wait_event(e)
         del prev_dec
 
-    def encode_stream(self, dev, n_decoders):
-        """A stream for encodes that run beside a decode (EncodeJob pipelining): confined to the SM group
-        of the row builders, so that its persistent conv kernels never sit on the decoders' SMs."""
-        self._rgb_streams(dev, n_decoders)
-        return self._rgb_stream_cache[(str(dev), n_decoders)][2]
+    def encode_stream(self, dev, n_decoders, n_lanes=1):
+        """A stream for encodes that run beside decodes (EncodeJob pipelining): confined to the SM group of
+        the row builders, so that its persistent conv kernels never sit on the decoders' SMs."""
+        return self.lanes(dev, n_decoders, n_lanes)[1]
 
-    def _rgb_streams(self, dev, n_decoders):
-        """(row-builder streams, decoder streams), three each.  The decoder streams own a group of SMs
-        (one SM per two decoder CTAs, up to half the GPU; l3c_partition_streams) and the row builders
-        get the rest: a latency-bound decoder warp that shares its SM with row-builder warps runs
-        ~1.5x slower.  L3C_SM_PARTITION=0, or a driver without green contexts, gives ordinary streams."""
-        key = (str(dev), n_decoders)
-        cache = self.__dict__.setdefault('_rgb_stream_cache', {})
+    def lanes(self, dev, n_decoders, n_lanes=1):
+        """-> ([DecodeLane] * n_lanes, encode stream).  A DecodeLane is the set of streams ONE decode in flight
+        uses: `main` (decoder networks, CDF rows of the bottleneck scales), `bld[3]` (CDF-row builders of the
+        R, G, B channels), `dec[3]` (the range decoders).  The `dec` streams of all lanes own a group of SMs
+        (driver green contexts, l3c_partition_streams) sized for `L3C_DEC_WARPS_PER_SM` decoder-kernel warps
+        per SM (default 4 = one latency-bound warp per SM sub-partition; a decoder warp that shares its
+        scheduler with throughput-bound warps runs ~1.5x slower); everything else -- including the encode
+        stream, which has the lowest priority -- runs on the remaining SMs.  Several lanes = several batches
+        being decoded side by side: the decode of ONE batch is bound by the serial chain of its range coder
+        and keeps only ~1/6 of the GPU busy.  L3C_SM_PARTITION=0, a driver without green contexts or an
+        attached profiler give ordinary streams (slower, same bytes)."""
+        key = (str(dev), n_decoders, n_lanes)
+        cache = self.__dict__.setdefault('_lane_cache', {})
         if key not in cache:
             part = None
             want_part = os.environ.get('L3C_SM_PARTITION', '1') != '0'
@@ -373,22 +385,56 @@ class BatchCodec(object):
                 want_part = False
             if want_part:
                 n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-                # two decoder CTAs per SM (measured at 16 x 512^2: 48 / 24 / 16 SMs -> decode 95 / 86 / 93 ms)
-                want = min(max(8, -(-n_decoders // 16) * 8), (n_sm // 16) * 8)
+                wps = int(os.environ.get('L3C_DEC_WARPS_PER_SM', 4))
+                # every stream = decoder warp + helper warp (measured at 16 x 512^2, one lane, 4 warps per SM:
+                # 48 / 24 / 16 SMs -> decode 95 / 86 / 93 ms)
+                want = -(-(2 * n_decoders * n_lanes) // (8 * wps)) * 8
+                want = min(max(8, want), (n_sm // 16) * 8)
                 want = int(os.environ.get('L3C_DEC_SMS', want))           # bring-up knob
-                part = E.partition_streams(dev, want, 3, 4)
-            if part is not None:
-                cache[key] = (part[1][:3], part[0], part[1][3])
-            else:
-                cache[key] = ([torch.cuda.Stream(device=dev) for _ in range(3)],
-                              [torch.cuda.Stream(device=dev) for _ in range(3)], torch.cuda.Stream(device=dev))
-        return cache[key][:2]
+                part = E.partition_streams(dev, want, 3 * n_lanes, 4 * n_lanes + 1)
+            lanes = []
+            for i in range(n_lanes):
+                ln = DecodeLane()
+                if part is not None:
+                    a, b = part[0], part[1]
+                    ln.dec = a[3 * i:3 * i + 3]
+                    ln.main = b[4 * i]
+                    ln.bld = b[4 * i + 1:4 * i + 4]
+                    ln.partitioned = True
+                else:
+                    ln.dec = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(3)]
+                    ln.bld = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(3)]
+                    ln.main = torch.cuda.Stream(device=dev, priority=-1)
+                    ln.partitioned = False
+                lanes.append(ln)
+            enc = part[1][4 * n_lanes] if part is not None else torch.cuda.Stream(device=dev)
+            cache[key] = (lanes, enc)
+        return cache[key]
+
+    def _on_decoder_stream(self, lane, fn):
+        """Run the launches of `fn` on the lane's first decoder stream (the decoders' SM group), ordered
+        after what the current stream has queued and before what it queues next."""
+        if lane is None or not lane.partitioned:
+            return fn()
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        with torch.cuda.stream(lane.dec[0]):
+            lane.dec[0].wait_event(ev)
+            out = fn()
+            done = torch.cuda.Event()
+            done.record(lane.dec[0])
+        cur.wait_event(done)
+        return out
 
     @_on_device
-    def decode_device(self, blob, offs, lens, shapes):
+    def decode_device(self, blob, offs, lens, shapes, lane=None):
         """Decode streams that already sit in HBM: `blob` uint8 device buffer (readable 4 bytes past
         every stream), offs/lens int64 [N][streams per image] in container order (coarse -> fine,
-        channel-major), shapes [(C,H,W)] coarse -> fine.  Returns uint8 [N,3,H,W] on the device."""
+        channel-major), shapes [(C,H,W)] coarse -> fine.  Returns uint8 [N,3,H,W] on the device.
+        `lane` (self.lanes()): the stream set of this decode when several decodes are in flight; the caller
+        has made `lane.main` the current stream.  Without it the range decoders of the bottleneck scales run
+        on the current stream and the RGB scale on lane 0 of a one-lane partition."""
         dev = blob.device
         N = offs.shape[0]
         if len(shapes) != self.net.scales + 1:
@@ -414,7 +460,7 @@ class BatchCodec(object):
                 row_dev = self._uniform(dmll.L, dev)[1]
                 d['table'][:] = row_dev.data_ptr()
                 d['row_pitch'][:] = 0
-                E.ac_decode_streams(desc, dev, dmll.L)
+                self._on_decoder_stream(lane, lambda: E.ac_decode_streams(desc, dev, dmll.L))
             else:
                 l, F_prev = self.net.get_P_nhwc(scale, bn8, F_prev if self.net._fuse_feat else None)
                 self._mark('net%d' % scale)
@@ -427,10 +473,10 @@ class BatchCodec(object):
                 d['row_pitch'][:] = pitch
                 tg = dmll.targets(dev)
                 if dmll.rgb_scale:
-                    self._decode_rgb_pipelined(l, S, tg, C, K, dmll.L, table, d, dev)
+                    self._decode_rgb_pipelined(l, S, tg, C, K, dmll.L, table, d, dev, lane=lane)
                 else:
                     E.dmll_build_table(l, S, tg, C, K, dmll.L, False, -1, table)
-                    E.ac_decode_streams(desc, dev, dmll.L)
+                    self._on_decoder_stream(lane, lambda: E.ac_decode_streams(desc, dev, dmll.L))
             self._mark('uniform' if uniform else ('rgb' if dmll.rgb_scale and scale == 0 else 'S%d' % scale))
             if scale > 0:
                 bn8 = E.symbols_to_values(S, self._symbol_values(scale, dmll, dev), self._rgb_shift(dev))

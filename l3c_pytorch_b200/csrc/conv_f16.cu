@@ -92,13 +92,24 @@ __device__ __forceinline__ void quad_transpose(uint32_t (&v)[4], int tq) {
     }
 }
 
+// KIND 0: 3x3 stride 1 (any dilation), weights resident.
+// KIND 1: 5x5 stride 2 (the down-sampling conv of every encoder, net.py:101): the input box of a tap is read
+//   with TMA element strides (2, 2), so the A operand of an 8x16 OUTPUT tile is again 128 dense rows of 128 B;
+//   for a filter column kx the taps ky = 0,2,4 (and ky = 1,3) share one strided box of 10 rows read at row
+//   offsets j*2048 B.  25 taps x 8 KB of weights do not fit beside the stages: every unit (kx, row parity)
+//   brings its 3 (2) weight slabs along with its box.  10 units, 100 MMAs per tile.
+constexpr int K5_A_BYTES = 10 * TW * 128;                  // 20480: strided halo box
+constexpr int K5_STAGE_BYTES = K5_A_BYTES + 3 * W_TAP_BYTES;   // 45056: box + up to three weight slabs
+
+template <int KIND>
 __global__ void __launch_bounds__(THREADS, 1)
-conv3x3_f16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                   const Params p, const int n_stages, const int a_bytes, const int ptiles) {
+conv_f16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                const Params p, const int n_stages, const int a_bytes, const int ptiles) {
+    constexpr int W_RES = (KIND == 0) ? W_RES_BYTES : 0;    // resident weights
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     // [weights 72 KB][pipe 0 stages][pipe 1 stages][barriers]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + W_RES_BYTES + PIPES * n_stages * a_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + W_RES + PIPES * n_stages * a_bytes);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + PIPES * BARS_PER_PIPE + 1);
 
     const int warp = threadIdx.x >> 5;
@@ -136,9 +147,9 @@ conv3x3_f16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     if (warp < PIPES) {
         // ===================== TMA producer of pipe `warp` =====================
         const int k = warp;
-        const uint32_t a_base = w_base + W_RES_BYTES + k * n_stages * a_bytes;
+        const uint32_t a_base = w_base + W_RES + k * n_stages * a_bytes;
         const uint32_t full0 = bar_base + 8u * (BARS_PER_PIPE * k), empty0 = full0 + 8u * MAX_STAGES;
-        if (k == 0 && lane == 0) {
+        if (KIND == 0 && k == 0 && lane == 0) {
             mbar_expect_tx(wbar, W_RES_BYTES);
             for (int tap = 0; tap < 9; ++tap)         // rows [tap][cout_pad] of the weight image
                 tma_load_2d(w_base + tap * W_TAP_BYTES, &map_w, wbar, 0, tap * (int)gridDim.y * 64 + ct * 64);
@@ -149,12 +160,23 @@ conv3x3_f16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             const int tx = q % p.tiles_x; q /= p.tiles_x;
             const int ty = q % p.tiles_y; q /= p.tiles_y;
             const int n = q;
-            for (int dx = 0; dx < 3; ++dx) {
+            constexpr int UNITS = (KIND == 0) ? 3 : 10;
+            for (int u = 0; u < UNITS; ++u) {
                 if (lane == 0) {
                     mbar_wait(empty0 + 8u * stage, phase ^ 1u);
-                    mbar_expect_tx(full0 + 8u * stage, a_bytes);
-                    tma_load_4d(a_base + stage * a_bytes, &map_x, full0 + 8u * stage, 0,
-                                tx * TW + (dx - 1) * d, ty * TH - d, n);
+                    const uint32_t dst = a_base + stage * a_bytes, bar = full0 + 8u * stage;
+                    if (KIND == 0) {
+                        mbar_expect_tx(bar, a_bytes);
+                        tma_load_4d(dst, &map_x, bar, 0, tx * TW + (u - 1) * d, ty * TH - d, n);
+                    } else {
+                        const int kx = u >> 1, par = u & 1, ntaps = 3 - par;
+                        mbar_expect_tx(bar, K5_A_BYTES + ntaps * W_TAP_BYTES);
+                        // input pixel of output (oy, ox), tap (ky, kx): (2*oy + ky - 2, 2*ox + kx - 2)
+                        tma_load_4d(dst, &map_x, bar, 0, 2 * tx * TW + kx - 2, 2 * ty * TH + par - 2, n);
+                        for (int j = 0; j < ntaps; ++j)
+                            tma_load_2d(dst + K5_A_BYTES + j * W_TAP_BYTES, &map_w, bar, 0,
+                                        ((par + 2 * j) * 5 + kx) * (int)gridDim.y * 64 + ct * 64);
+                    }
                 }
                 __syncwarp();
                 if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1u; }
@@ -163,32 +185,44 @@ conv3x3_f16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     } else if (warp < 2 * PIPES) {
         // ===================== MMA issuer of pipe `warp - PIPES` (warp-uniform code) =====================
         const int k = warp - PIPES;
-        const uint32_t a_base = w_base + W_RES_BYTES + k * n_stages * a_bytes;
+        const uint32_t a_base = w_base + W_RES + k * n_stages * a_bytes;
         const uint32_t full0 = bar_base + 8u * (BARS_PER_PIPE * k), empty0 = full0 + 8u * MAX_STAGES;
         const uint32_t tfull0 = full0 + 8u * (2 * MAX_STAGES), tempty0 = tfull0 + 16u;
         constexpr uint32_t IDESC = idesc_f16(64);
         uint32_t stage = 0, phase = 0;
         uint32_t acc = 0, acc_phase = 0;
-        mbar_wait(wbar, 0);
+        if (KIND == 0) mbar_wait(wbar, 0);
         for (int t = blockIdx.x + k * gridDim.x; t < ptiles; t += PIPES * gridDim.x) {
             mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);       // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (k * 2 + acc) * ACC_COLS;
-            for (int dx = 0; dx < 3; ++dx) {
+            constexpr int UNITS = (KIND == 0) ? 3 : 10;
+            for (int u = 0; u < UNITS; ++u) {
                 mbar_wait(full0 + 8u * stage, phase);
                 tc_fence_after();
                 const uint32_t a0 = a_base + stage * a_bytes;
                 if (elect_one()) {
+                    if (KIND == 0) {
 #pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) {
-                        const uint64_t da = make_desc(a0 + dy * d * (TW * 128));           // dy*d rows of 16 px
-                        const uint64_t db = make_desc(w_base + (dy * 3 + dx) * W_TAP_BYTES);
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint64_t da = make_desc(a0 + dy * d * (TW * 128));           // dy*d rows of 16 px
+                            const uint64_t db = make_desc(w_base + (dy * 3 + u) * W_TAP_BYTES);
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)                                     // +32 B = 16 fp16 along K
-                            mma_f16(d_tmem, da + 2u * kk, db + 2u * kk, IDESC, (dx | dy | kk) != 0 ? 1u : 0u);
+                            for (int kk = 0; kk < 4; ++kk)                                     // +32 B = 16 fp16 along K
+                                mma_f16(d_tmem, da + 2u * kk, db + 2u * kk, IDESC, (u | dy | kk) != 0 ? 1u : 0u);
+                        }
+                    } else {
+                        const int ntaps = 3 - (u & 1);
+                        for (int j = 0; j < ntaps; ++j) {
+                            const uint64_t da = make_desc(a0 + j * (TW * 128));                // box row j = tap ky0 + 2j
+                            const uint64_t db = make_desc(a0 + K5_A_BYTES + j * W_TAP_BYTES);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                mma_f16(d_tmem, da + 2u * kk, db + 2u * kk, IDESC, (u | j | kk) != 0 ? 1u : 0u);
+                        }
                     }
                     mma_commit(empty0 + 8u * stage);              // frees the stage when the MMAs retire
-                    if (dx == 2) mma_commit(tfull0 + 8u * acc);   // accumulator complete -> epilogue
+                    if (u == UNITS - 1) mma_commit(tfull0 + 8u * acc);   // accumulator complete -> epilogue
                 }
                 __syncwarp();
                 if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1u; }
@@ -282,14 +316,25 @@ conv3x3_f16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         const int oy = ty * TH + 2 * quarter + lh, ox = tx * TW + tr + 8 * rh;
                         const size_t W2 = 2 * (size_t)p.W;
                         const size_t row0 = ((size_t)n * (2 * p.H) + 2 * oy) * W2 + 2 * ox;   // output pixel (si=0, sj=0)
-                        if (p.y != nullptr && inside) {
+                        if (p.y != nullptr) {
+                            // same transpose on the fp32 values: thread tq then owns conv channels c0 + 0..7
+                            // (c0 = cb + 8*tq) = output channels cq0, cq0 + 1 of the four sub-pixels, and a quad
+                            // writes 32 contiguous bytes per output pixel
+                            uint32_t fa[4], fb[4];
 #pragma unroll
-                            for (int jb = 0; jb < 4; ++jb) {
-                                const int co = cb + 8 * jb + 2 * tq;          // even: (co, co+1) -> sj = 0 / 1
-                                const int cq = co >> 2, si = (co >> 1) & 1;
-                                const size_t o2 = (row0 + si * W2) * p.y_pitch + p.y_coff + cq;
-                                p.y[o2] = a[jb];
-                                p.y[o2 + p.y_pitch] = b[jb];
+                            for (int jb = 0; jb < 4; ++jb) { fa[jb] = __float_as_uint(a[jb]); fb[jb] = __float_as_uint(b[jb]); }
+                            quad_transpose(fa, tq);           // fa[s] = channel c0 + 2s, fb[s] = channel c0 + 2s + 1
+                            quad_transpose(fb, tq);
+                            if (inside) {
+                                const int cq0 = (cb + 8 * tq) >> 2;
+#pragma unroll
+                                for (int si = 0; si < 2; ++si) {
+                                    const size_t o2 = (row0 + si * W2) * p.y_pitch + p.y_coff + cq0;
+                                    *reinterpret_cast<float2 *>(p.y + o2) =
+                                        make_float2(__uint_as_float(fa[si]), __uint_as_float(fa[2 + si]));        // sj = 0
+                                    *reinterpret_cast<float2 *>(p.y + o2 + p.y_pitch) =
+                                        make_float2(__uint_as_float(fb[si]), __uint_as_float(fb[2 + si]));        // sj = 1
+                                }
                             }
                         }
                         if (p.yh != nullptr) {
@@ -493,10 +538,11 @@ conv1x1_f16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 int conv2d_f16(const l3c_conv_t &p, cudaStream_t st) {
     using namespace f16;
     const bool k3 = p.ksize == 3 && p.stride == 1 && p.Cin == 64 && p.x_pitch == 64;
+    const bool k5 = p.ksize == 5 && p.stride == 2 && p.dilation == 1 && p.Cin == 64 && p.x_pitch == 64;
     const bool k1 = p.ksize == 1 && p.stride == 1 && p.Cin % 64 == 0 && p.x_pitch == p.Cin &&
                     !(p.flags & L3C_CONV_PIXEL_SHUFFLE2);
-    L3C_REQUIRE(k3 || k1, "l3c_conv2d[f16]: tensor-core path needs 3x3/Cin=64 or 1x1/Cin%%64==0, stride 1, dense "
-                          "input pitch (got k=%d s=%d Cin=%d pitch=%d)", p.ksize, p.stride, p.Cin, p.x_pitch);
+    L3C_REQUIRE(k3 || k5 || k1, "l3c_conv2d[f16]: tensor-core path needs 3x3/s1/Cin=64, 5x5/s2/Cin=64 or 1x1/Cin%%64==0, "
+                                "dense input pitch (got k=%d s=%d Cin=%d pitch=%d)", p.ksize, p.stride, p.Cin, p.x_pitch);
     L3C_REQUIRE(p.x_h && p.w_h, "l3c_conv2d[f16]: x_h / w_h (fp16 operand images) are required");
     L3C_REQUIRE(p.y || p.y_h, "l3c_conv2d[f16]: no output");
     L3C_REQUIRE(p.cout_pad % 64 == 0 && p.cout_pad >= p.Cout, "l3c_conv2d[f16]: cout_pad=%d", p.cout_pad);
@@ -506,7 +552,8 @@ int conv2d_f16(const l3c_conv_t &p, cudaStream_t st) {
     const int n_sm = stream_sm_count(st);          // the stream may be confined to a group of SMs
     static bool configured = false;
     if (!configured) {
-        L3C_CUDA(cudaFuncSetAttribute(conv3x3_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        L3C_CUDA(cudaFuncSetAttribute(conv_f16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        L3C_CUDA(cudaFuncSetAttribute(conv_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         L3C_CUDA(cudaFuncSetAttribute(conv1x1_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
@@ -557,8 +604,53 @@ int conv2d_f16(const l3c_conv_t &p, cudaStream_t st) {
         if (per_ct < 1) per_ct = 1;
         if (per_ct > ptiles) per_ct = ptiles;
         const int smem_bytes = W_RES_BYTES + PIPES * n_stages * a_bytes + 1024 + 512;
-        conv3x3_f16_kernel<<<dim3(per_ct, cout_tiles), THREADS, smem_bytes, st>>>(map_x, map_w, q, n_stages, a_bytes, ptiles);
+        conv_f16_kernel<0><<<dim3(per_ct, cout_tiles), THREADS, smem_bytes, st>>>(map_x, map_w, q, n_stages, a_bytes, ptiles);
         L3C_LAUNCH_CHECK("conv3x3_f16_kernel");
+        return L3C_OK;
+    }
+    if (k5) {
+        L3C_REQUIRE(p.Cout % 64 == 0, "l3c_conv2d[f16]: 5x5/s2 layers need Cout %% 64 == 0 (got %d)", p.Cout);
+        L3C_REQUIRE(!(p.flags & L3C_CONV_PIXEL_SHUFFLE2) && p.y_pitch % 8 == 0 && p.y_coff % 8 == 0,
+                    "l3c_conv2d[f16]: 5x5/s2 output pitch/offset alignment (pitch=%d coff=%d)", p.y_pitch, p.y_coff);
+        const int Ho = (p.H + 4 - 5) / 2 + 1, Wo = (p.W + 4 - 5) / 2 + 1;
+        {
+            // element strides (2, 2): the box visits every second pixel / row; box sizes are given in
+            // traversed elements (16 px -> 32, 10 rows -> 20)
+            cuuint64_t dims[4] = {64, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+            cuuint64_t strides[3] = {128, (cuuint64_t)p.W * 128, (cuuint64_t)p.H * p.W * 128};
+            cuuint32_t box[4] = {64, 2 * TW, 20, 1};
+            cuuint32_t estr[4] = {1, 2, 2, 1};
+            CUresult r = encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(p.x_h), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            L3C_REQUIRE(r == CUDA_SUCCESS, "l3c_conv2d[f16]: cuTensorMapEncodeTiled(x, 5x5/s2) failed with %d", (int)r);
+        }
+        {
+            cuuint64_t dims[2] = {64, (cuuint64_t)25 * p.cout_pad};
+            cuuint64_t strides[1] = {128};
+            cuuint32_t box[2] = {64, 64};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = encode(&map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(p.w_h), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            L3C_REQUIRE(r == CUDA_SUCCESS, "l3c_conv2d[f16]: cuTensorMapEncodeTiled(w, 5x5/s2) failed with %d", (int)r);
+        }
+        Params q;
+        q.bias = p.bias; q.residual = p.residual; q.y = p.y; q.yh = reinterpret_cast<__half *>(p.y_h);
+        q.N = p.N; q.H = Ho; q.W = Wo;                      // the epilogue works on OUTPUT pixels
+        q.Cout = p.Cout; q.y_pitch = p.y_pitch; q.y_coff = p.y_coff;
+        q.dilation = 1; q.flags = p.flags;
+        q.tiles_x = ceil_div(Wo, TW);
+        q.tiles_y = ceil_div(Ho, TH);
+        const int cout_tiles = p.cout_pad / 64;
+        const int ptiles = p.N * q.tiles_x * q.tiles_y;
+        int per_ct = n_sm / cout_tiles;
+        if (per_ct < 1) per_ct = 1;
+        if (per_ct > ptiles) per_ct = ptiles;
+        const int n_stages = 2;
+        const int smem_bytes = PIPES * n_stages * K5_STAGE_BYTES + 1024 + 512;
+        conv_f16_kernel<1><<<dim3(per_ct, cout_tiles), THREADS, smem_bytes, st>>>(map_x, map_w, q, n_stages, K5_STAGE_BYTES, ptiles);
+        L3C_LAUNCH_CHECK("conv5x5s2_f16_kernel");
         return L3C_OK;
     }
     // ---- 1x1

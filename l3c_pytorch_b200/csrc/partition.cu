@@ -54,7 +54,7 @@ struct Partition {
     int device = -1, sm_request = 0;
     int sm_a = 0, sm_b = 0;
     CUgreenCtx ctx_a = nullptr, ctx_b = nullptr;
-    std::vector<CUstream> streams_a, streams_b;
+    std::vector<CUstream> streams_a, streams_b, streams_b_low;
 };
 
 std::mutex g_mu;
@@ -75,6 +75,8 @@ int stream_sm_count(cudaStream_t st) {
             for (CUstream s : p->streams_a)
                 if ((cudaStream_t)s == st) return p->sm_a;
             for (CUstream s : p->streams_b)
+                if ((cudaStream_t)s == st) return p->sm_b;
+            for (CUstream s : p->streams_b_low)
                 if ((cudaStream_t)s == st) return p->sm_b;
         }
     }
@@ -128,12 +130,12 @@ extern "C" int l3c_partition_streams(int sm_a, int n_a, void **streams_a, int n_
         g_parts.push_back(p);
         part = p;
     }
-    // group B: the first three streams (CDF-row builders of a decode) outrank any further ones (used
-    // for work that merely runs beside a decode, e.g. the encode of the next batch)
-    auto grow = [&](std::vector<CUstream> &v, CUgreenCtx ctx, int n, int n_high) -> bool {
+    // group B: all streams but the LAST one are high priority (CDF-row builders and decoder networks of the
+    // decodes in flight); the last one has default priority (work that merely runs beside the decodes: the
+    // encode of the next batch)
+    auto grow = [&](std::vector<CUstream> &v, CUgreenCtx ctx, int n, int priority) -> bool {
         while ((int)v.size() < n) {
             CUstream s = nullptr;
-            const int priority = ((int)v.size() < n_high) ? -1 : 0;
             if (drv.GreenCtxStreamCreate(&s, ctx, CU_STREAM_NON_BLOCKING, priority) != CUDA_SUCCESS) return false;
             // the runtime must accept the stream: one empty launch, checked
             partition_probe_kernel<<<1, 32, 0, (cudaStream_t)s>>>(nullptr);
@@ -142,12 +144,14 @@ extern "C" int l3c_partition_streams(int sm_a, int n_a, void **streams_a, int n_
         }
         return true;
     };
-    if (!grow(part->streams_a, part->ctx_a, n_a, 64) || !grow(part->streams_b, part->ctx_b, n_b, 3)) {
+    if (!grow(part->streams_a, part->ctx_a, n_a, -1) || !grow(part->streams_b, part->ctx_b, n_b - 1, -1) ||
+        !grow(part->streams_b_low, part->ctx_b, n_b > 0 ? 1 : 0, 0)) {
         set_error("l3c_partition_streams: could not create / use a partition stream on device %d", dev);
         return L3C_EUNSUPPORTED;
     }
     for (int i = 0; i < n_a; ++i) streams_a[i] = (void *)part->streams_a[i];
-    for (int i = 0; i < n_b; ++i) streams_b[i] = (void *)part->streams_b[i];
+    for (int i = 0; i + 1 < n_b; ++i) streams_b[i] = (void *)part->streams_b[i];
+    if (n_b > 0) streams_b[n_b - 1] = (void *)part->streams_b_low[0];
     if (sm_a_out) *sm_a_out = part->sm_a;
     if (sm_b_out) *sm_b_out = part->sm_b;
     return L3C_OK;

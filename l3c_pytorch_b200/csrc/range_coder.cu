@@ -20,6 +20,8 @@
 //     r -> 2r+1, dv -> 2dv+bit, so `high`, `value` and the MSB fix-ups leave the chain;
 //   * coder state can be saved/restored so that a stream may be decoded in chunks while later CDF
 //     rows are still being built (RGB channel pipelining).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace l3c {
@@ -737,24 +739,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!done);
 }
 
-__global__ void __launch_bounds__(64)
-ac_decode256_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, uint32_t first, uint32_t count) {
-    __shared__ __align__(16) uint4 ring[R][2][32];      // proposals: [slot][half][lane]
-    __shared__ uint32_t tops[R];                        // winning proposal per slot (decoder -> helper)
-    __shared__ __align__(8) uint64_t bars[4];           // full[0..1], empty[0..1]
+// SPC = streams per CTA.  Decoder warps are warps 0..SPC-1, helper warps SPC..2*SPC-1: with SPC = 4 the
+// decoder and the helper of a stream sit on the same SM sub-partition (warp id mod 4) and every scheduler
+// serves exactly one latency-bound decoder warp -- a CTA of 4 streams fills one SM, so a batch of 48
+// streams needs 12 SMs and several batches can be decoded side by side.
+constexpr int RING_BYTES = R * 2 * 32 * 16;           // 16 KB of proposals per stream
+constexpr int STREAM_SMEM = RING_BYTES + 128;         // + tops[R] (64 B) + 4 mbarriers (32 B), 16-byte aligned
 
-    const int sid = blockIdx.x;
-    if (sid >= n_streams) return;
-    const int warp = threadIdx.x >> 5;
+template <int SPC>
+__global__ void __launch_bounds__(64 * SPC)
+ac_decode256_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, uint32_t first, uint32_t count) {
+    extern __shared__ __align__(16) uint8_t dec_smem[];
+    const int warp_id = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const l3c_dec_stream_t st = streams[sid];
-    const uint32_t n = st.n_sym;
-    if (first >= n) return;
-    const uint32_t last = (count > n - first) ? n : first + count;   // exclusive
-    const uint32_t n_groups = (last - first + G - 1) / G;
+    const int sslot = warp_id % SPC;                    // stream slot inside the CTA
+    const int warp = warp_id / SPC;                     // 0 = decoder, 1 = helper
+    uint8_t *mine = dec_smem + sslot * STREAM_SMEM;
+    uint4 (*ring)[2][32] = reinterpret_cast<uint4 (*)[2][32]>(mine);          // proposals: [slot][half][lane]
+    uint32_t *tops = reinterpret_cast<uint32_t *>(mine + RING_BYTES);         // winning proposal per slot (decoder -> helper)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(mine + RING_BYTES + 64);    // full[0..1], empty[0..1]
 
     const uint32_t bar0 = smem_u32(bars);
-    if (threadIdx.x == 0) {
+    if (warp == 0 && lane == 0) {
         mbar_init(bar0 + 0, 32);
         mbar_init(bar0 + 8, 32);
         mbar_init(bar0 + 16, 32);
@@ -762,6 +768,14 @@ ac_decode256_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+
+    const int sid = blockIdx.x * SPC + sslot;
+    if (sid >= n_streams) return;
+    const l3c_dec_stream_t st = streams[sid];
+    const uint32_t n = st.n_sym;
+    if (first >= n) return;
+    const uint32_t last = (count > n - first) ? n : first + count;   // exclusive
+    const uint32_t n_groups = (last - first + G - 1) / G;
 
     if (warp == 1) {
         // ============================ helper warp ============================
@@ -996,7 +1010,20 @@ extern "C" int l3c_ac_decode_streams(const l3c_dec_stream_t *streams_dev, int n_
     if (L <= 32) {
         ac_decode32_kernel<<<grid, blk, 0, st>>>(streams_dev, n_streams, L, first, count);
     } else if (L == 256) {
-        v3::ac_decode256_kernel<<<n_streams, 64, 0, st>>>(streams_dev, n_streams, first, count);
+        static int spc = 0;
+        if (spc == 0) {
+            const char *e = getenv("L3C_DEC_SPC");
+            spc = e ? atoi(e) : 1;
+            if (spc != 1 && spc != 2 && spc != 4) spc = 1;
+            L3C_CUDA(cudaFuncSetAttribute(v3::ac_decode256_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          4 * v3::STREAM_SMEM));
+        }
+        if (spc == 4)
+            v3::ac_decode256_kernel<4><<<ceil_div(n_streams, 4), 256, 4 * v3::STREAM_SMEM, st>>>(streams_dev, n_streams, first, count);
+        else if (spc == 2)
+            v3::ac_decode256_kernel<2><<<ceil_div(n_streams, 2), 128, 2 * v3::STREAM_SMEM, st>>>(streams_dev, n_streams, first, count);
+        else
+            v3::ac_decode256_kernel<1><<<n_streams, 64, v3::STREAM_SMEM, st>>>(streams_dev, n_streams, first, count);
     } else {
         ac_decode_kernel<8, false><<<grid, blk, 0, st>>>(streams_dev, n_streams, L, first, count);
     }

@@ -92,6 +92,19 @@ class DiscretizedMixLogisticLoss(nn.Module):
         pi, mu, ls = E.dmll_channel_params(lh, xd, C, K, self.rgb_scale, c_cur)
         return CDFOut(pi, mu, ls, K, targets.to(l.device))
 
+    def sample(self, l, C, u_sel=None, u_x=None):
+        """logistic_mixture.py:143-144,277-323: one sample per sub-pixel.  l: NKpHW-shaped tensor -> NCHW float
+        (RGB: clamped to [0, 255], not rounded).  u_sel [N,C,K,H,W] / u_x [N,C,H,W]: the uniform random
+        numbers (default: drawn here from the device generator, in [1e-5, 1 - 1e-5] as in the reference)."""
+        lh = self._nhwc(l)
+        N, H, W, Kp = lh.shape
+        K = non_shared_get_K(Kp, C)
+        if u_sel is None:
+            u_sel = torch.empty(N, C, K, H, W, dtype=torch.float32, device=lh.device).uniform_(1e-5, 1. - 1e-5)
+        if u_x is None:
+            u_x = torch.empty(N, C, H, W, dtype=torch.float32, device=lh.device).uniform_(1e-5, 1. - 1e-5)
+        return E.dmll_sample(lh.contiguous(), u_sel, u_x, C, K, self.use_coeffs)
+
     def nll_sum(self, sym_u8, l_nhwc, want_map=False):
         """per-image NLL in nats (float64 [N]) of uint8 symbol planes under NHWC parameters."""
         C = sym_u8.shape[1]

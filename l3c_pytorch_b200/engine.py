@@ -121,18 +121,18 @@ class PackedConv(object):
 
 
 def _get_f16(self):
-    """F16 tensor-core operand image (conv_f16.cu): 3x3 -> [9 taps][cout_pad][64 cin] fp16, 1x1 ->
+    """F16 tensor-core operand image (conv_f16.cu): 3x3 / 5x5 -> [taps][cout_pad][64 cin] fp16, 1x1 ->
     [Cin/64][cout_pad][64] fp16; K-major rows of 128 B; values rounded to FP16 (RN, saturating)."""
     _, b = self.get()
     if getattr(self, 'w_h', None) is None:
         w = self.conv.weight.detach().float().clamp(-65504.0, 65504.0)
         cout, cin, kh, kw = w.shape
         cout_pad = (cout + 63) // 64 * 64
-        assert cin % 64 == 0 and kh == kw and kh in (1, 3)
-        if kh == 3:
+        assert cin % 64 == 0 and kh == kw and kh in (1, 3, 5)
+        if kh in (3, 5):
             assert cin == 64
-            img = torch.zeros(9, cout_pad, 64, dtype=torch.float16, device=w.device)
-            img[:, :cout] = w.permute(2, 3, 0, 1).reshape(9, cout, 64).half()
+            img = torch.zeros(kh * kh, cout_pad, 64, dtype=torch.float16, device=w.device)
+            img[:, :cout] = w.permute(2, 3, 0, 1).reshape(kh * kh, cout, 64).half()
         else:
             img = torch.zeros(cin // 64, cout_pad, 64, dtype=torch.float16, device=w.device)
             img[:, :cout] = w.reshape(cout, cin // 64, 64).permute(1, 0, 2).half()
@@ -272,7 +272,7 @@ def conv2d(conv, x, cin=None, relu=False, residual=None, pixel_shuffle=False, ou
 
 def _conv2d_f16(conv, xa, cin, relu, residual, pixel_shuffle, out, out_coff, want):
     """conv2d in precision mode 'f16': tensor-core-eligible layers read the FP16 operand image `xa.r` and
-    run conv_f16.cu; the others (5x5/s2, Cin = 3 or 5) run the fp32 FFMA kernel on `xa.f`.  Either kernel
+    run conv_f16.cu; the others (Cin = 3 or 5) run the fp32 FFMA kernel on `xa.f`.  Either kernel
     writes what the consumers need: fp32 (`want` 'plain' / 'act') and / or the FP16 image ('act' / 'round')."""
     src = xa.f if xa.f is not None else xa.r
     require_cuda(src, 'x')
@@ -297,9 +297,11 @@ def _conv2d_f16(conv, xa, cin, relu, residual, pixel_shuffle, out, out_coff, wan
             assert out.dtype == torch.float32
             y = out
     k = kh
-    tc = (stride == 1 and xp == conv.in_channels and cin == conv.in_channels and
-          ((k == 3 and cin == 64 and cout % 64 == 0) or
-           (k == 1 and cin % 64 == 0 and not pixel_shuffle and cout % 2 == 0 and cout <= 256 and residual is None)))
+    tc = (xp == conv.in_channels and cin == conv.in_channels and
+          ((k == 3 and stride == 1 and cin == 64 and cout % 64 == 0) or
+           (k == 5 and stride == 2 and dil == 1 and cin == 64 and cout % 64 == 0 and not pixel_shuffle) or
+           (k == 1 and stride == 1 and cin % 64 == 0 and not pixel_shuffle and cout % 2 == 0 and cout <= 256 and
+            residual is None)))
     if need_f and y is None:
         y = torch.empty(shape, dtype=torch.float32, device=src.device)
     if need_h and y_h is None:
@@ -458,6 +460,17 @@ def dmll_channel_params(l, x_dec, C, K, rgb, c):
                                       _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _stream_ptr()))
     LAUNCHES['n'] += 1
     return outs
+
+
+def dmll_sample(l, u_sel, u_x, C, K, rgb):
+    """l NHWC [N,H,W,Kp]; u_sel f32 [N,C,K,H,W]; u_x f32 [N,C,H,W] -> sampled values f32 [N,C,H,W]."""
+    N, H, W, _ = l.shape
+    assert u_sel.shape == (N, C, K, H, W) and u_x.shape == (N, C, H, W)
+    out = torch.empty(N, C, H, W, dtype=torch.float32, device=l.device)
+    check(lib.l3c_dmll_sample(_ptr(l), _ptr(u_sel.contiguous()), _ptr(u_x.contiguous()), N, H * W, C, K, int(rgb),
+                              _ptr(out), _stream_ptr()))
+    LAUNCHES['n'] += 1
+    return out
 
 
 # ----------------------------------------------------------------------------------------------

@@ -17,7 +17,7 @@ What it mirrors (flag names and meaning as in /root/reference/src/test.py:44-141
     weighted by their sub-pixel counts (test/multiscale_tester.py:283-345), cached per (test set, itr);
   * --write_to_files: every image through the real coder to `<name>.l3c`, decoded again and compared,
     real bpsp reported, per-stage times collected (test/multiscale_tester.py:347-373).
-Not built: --sample and --recursive (rows f2/f3); they raise NotImplementedError.
+--sample writes the ground truth and three sampled images per test image (row f3).
 
 B200-first difference: in the default mode images of equal size are pushed through the network as
 one batch (`--batch`, default 16) instead of one at a time.
@@ -182,6 +182,14 @@ def read_image_chw(path, crop=None):
     return torch.from_numpy(np.ascontiguousarray(a)).permute(2, 0, 1).contiguous()
 
 
+def save_png(img_1chw, path):
+    """1CHW tensor with values in [0, 255] -> PNG (uint8 truncation as in multiscale_tester.py:425-434)."""
+    from PIL import Image
+    assert img_1chw.shape[0] == 1 and img_1chw.shape[1] == 3, img_1chw.shape
+    a = img_1chw[0].detach().float().cpu().numpy().transpose(1, 2, 0).astype(np.uint8)
+    Image.fromarray(np.ascontiguousarray(a)).save(path)
+
+
 class TestResult(object):
     def __init__(self, metric_name='bpsp'):
         self.metric_name = metric_name
@@ -201,6 +209,23 @@ def default_configs_dir():
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'configs')
 
 
+DEFAULT_RECURSIVE_FOR_RGB = 3        # multiscale_tester.py:50
+
+
+def parse_recursive_flag(recursive, config_ms):
+    """multiscale_tester.py:123-132: only the RGB baselines are evaluated recursively; 'auto' = 3 more
+    applications of the shared scale for RGB-shared (one trained scale)."""
+    if not config_ms.rgb_bicubic_baseline:
+        return 0
+    if recursive == 'auto':
+        if config_ms.rgb_bicubic_baseline and config_ms.num_scales == 1:
+            return DEFAULT_RECURSIVE_FOR_RGB
+    try:
+        return int(recursive)
+    except ValueError:
+        return 0
+
+
 class Tester(object):
     """One experiment (log date) at one checkpoint.  `make_blueprint(config_ms)` / `make_bitcoding(blueprint,
     times, compare_with_theory)` are injection points (defaults: the B200 classes)."""
@@ -208,14 +233,15 @@ class Tester(object):
     def __init__(self, log_date, flags, restore_itr, configs_dir=None, make_blueprint=None, make_bitcoding=None):
         from . import config as config_parser
         self.flags = flags
-        if getattr(flags, 'sample', None):
-            raise NotImplementedError('--sample (SURVEY section 8 row f3) is not built')
-        if str(getattr(flags, 'recursive', '0')) != '0':
-            raise NotImplementedError('--recursive (SURVEY section 8 row f2) is not built')
         self.experiment_dir = find_experiment_dir(flags.log_dir, log_date)
         self.log_date = log_date
         (ms_path, _dl_path), _postfix = configs_of_experiment(self.experiment_dir, configs_dir or default_configs_dir())
         self.config_ms = config_parser.parse(ms_path)[0]
+        self.recursive = parse_recursive_flag(getattr(flags, 'recursive', '0'), self.config_ms)
+        if flags.write_to_files and self.recursive:
+            raise NotImplementedError('--write_to_file not implemented for --recursive')   # multiscale_tester.py:187-188
+        if self.recursive:
+            print('--recursive={}'.format(self.recursive))
         if make_blueprint is None:
             from .blueprint import MultiscaleBlueprint
             make_blueprint = MultiscaleBlueprint
@@ -281,8 +307,9 @@ class Tester(object):
     # ---- default mode: theoretical bpsp, equal-sized images batched
     def _theory(self, testset):
         from . import auto_crop
-        result = TestResult('bpsp')
-        fac = 2 ** self.config_ms.num_scales
+        result = TestResult('bpsp recursive' if self.recursive else 'bpsp')
+        # multiscale_tester.py:222-225: every recursion halves the image once more
+        fac = 2 ** (self.recursive + 1) if self.recursive else 2 ** self.config_ms.num_scales
         batch_max = max(1, int(getattr(self.flags, 'batch', 16) or 1))
         combos = OrderedDict()                  # image name -> CropLossCombinator
         pending = OrderedDict()                 # (C,H,W) -> [(name, crop uint8 CHW)]
@@ -294,10 +321,13 @@ class Tester(object):
             raw = torch.stack([c for _, c in items])                       # N,C,H,W uint8
             n_sub = int(np.prod(raw.shape[1:]))
             img_batch, _ = self.blueprint.unpack_batch_pad(raw, fac=fac)
-            out = self.blueprint.forward(img_batch)
+            out = self.blueprint.forward(img_batch, self.recursive)
             per_image = self.blueprint.get_loss_per_image(out, num_subpixels_before_pad=n_sub)
             for (name, _), bpsp in zip(items, per_image):
                 combos[name].add(float(bpsp), n_sub)
+            if getattr(self.flags, 'sample', None):        # multiscale_tester.py:327-328 (one image at a time)
+                for (name, crop) in items:
+                    self._sample(name, crop, fac)
 
         for p in testset.ps:
             name = os.path.splitext(os.path.basename(p))[0]
@@ -314,6 +344,25 @@ class Tester(object):
             result[name] = comb.get_bpsp()
         print('{}: {} images: mean {}={}'.format(self.log_date, len(combos), result.metric_name, result.mean()))
         return result
+
+    # ---- --sample: images sampled from the model (multiscale_tester.py:436-448)
+    def _sample(self, name, raw_u8, fac):
+        out_dir = os.path.join(self.flags.sample, self.log_date)
+        os.makedirs(out_dir, exist_ok=True)
+        self._n_sampled = getattr(self, '_n_sampled', -1) + 1
+        prefix = '{}_{}'.format(self._n_sampled, name)
+        if any(f.startswith(prefix) for f in os.listdir(out_dir)):
+            raise FileExistsError('Previous sample outputs found in {}. Please remove.'.format(out_dir))
+        img_batch, _ = self.blueprint.unpack_batch_pad(raw_u8.unsqueeze(0), fac=fac)
+        out = self.blueprint.forward(img_batch)
+        bpsps = self.blueprint.get_loss(out).nonrecursive_bpsps
+        save_png(img_batch, os.path.join(out_dir, '{}_{:.3f}_gt.png'.format(prefix, sum(bpsps))))
+        for style, sample_scales in (('rgb', []),               # sample the RGB scale (final scale)
+                                     ('rgb+bn0', [0]),          # RGB + z^(1)
+                                     ('rgb+bn0+bn1', [0, 1])):  # RGB + z^(1) + z^(2)
+            sampled = self.blueprint.sample_forward(img_batch, sample_scales)
+            bpsp_sample = sum(bpsps[len(sample_scales) + 1:])
+            save_png(sampled, os.path.join(out_dir, '{}_{}_{:.3f}.png'.format(prefix, style, bpsp_sample)))
 
     # ---- --write_to_files: real files through the coder, decoded back and compared
     def _write_all(self, testset):

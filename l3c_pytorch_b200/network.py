@@ -112,7 +112,9 @@ class Head(nn.Module):
         self.head = conv(Cin, config_ms.Cf, config_ms.kernel_size)
 
     def forward(self, x):
-        return E.conv2d(self.head, x)
+        # the head output feeds nothing but the encoder's down-sampling conv: in f16 mode (where that conv runs
+        # on the tensor cores) only its FP16 operand image is written
+        return E.conv2d(self.head, x, want='round' if E.f16_mode() else 'plain')
 
 
 class RGBHead(nn.Module):
@@ -124,7 +126,7 @@ class RGBHead(nn.Module):
 
     def forward(self, t4):
         """t4: NHWC [N,H,W,4] = second MeanShift already applied by engine.rgb_prep."""
-        return E.conv2d(self.head[1].head, t4, cin=3)
+        return E.conv2d(self.head[1].head, t4, cin=3, want='act' if E.f16_mode() else 'plain')
 
 
 class Quantizer(nn.Module):
@@ -159,6 +161,11 @@ class EDSRLikeEnc(nn.Module):
         lo, hi = config_ms.q.levels_range
         self.levels = nn.Parameter(torch.linspace(lo, hi, self.L), requires_grad=False)
         self.q = Quantizer(self.levels, config_ms.q.sigma)
+
+    def quantize_x(self, x):
+        """net.py:132-134: hard-quantised values levels[argmin_l |x - level_l|] of an NCHW tensor (sampling only)."""
+        lev = self.levels.detach().float()
+        return lev[(x.unsqueeze(-1) - lev).abs().argmin(-1)]
 
     def forward(self, x):
         x = E.conv2d(self.down, x, want='act')
@@ -374,36 +381,90 @@ class MultiscaleNetwork(nn.Module):
 
     def forward(self, x, auto_recurse=0):
         """x: image batch NCHW in [0,255] (uint8 / long / float).  Eval-mode forward
-        (multiscale_network.py:226-306) -> Out."""
-        if auto_recurse:
-            raise NotImplementedError('auto_recurse is not on the bit-coding path '
-                                      '(multiscale_tester.py:187-188)')
+        (multiscale_network.py:226-306) -> Out.  auto_recurse: how many times the last trained scale is
+        applied again (theoretical-bpsp evaluation of the RGB-shared baseline, `--recursive`;
+        multiscale_network.py:235-238,291-294); the extra scales use scale index -1, never fuse decoder
+        features, and `Out.auto_recursive_from` marks where they start."""
         img = self._as_u8_planes(x)
-        out = Out(targets_style='S' if self._rgb else 'bn')
+        forward_scales = list(range(self.scales)) + [-1] * int(auto_recurse)
+        out = Out(targets_style='S' if self._rgb else 'bn',
+                  auto_recursive_from=self.scales if auto_recurse > 0 else None)
         out.append_input_image(img)
         enc_outs = []
         if self._rgb:
             inp = img
-            for s in range(self.scales):
+            for s in forward_scales:
                 eo = self.nets[s].enc(inp)
                 enc_outs.append(eo)
                 inp = eo.S
         else:
             _, inp = E.rgb_prep(img, self.sub_rgb_mean, self.heads[0].head[0])
-            for s in range(self.scales):
+            for s in forward_scales:
                 h = self.heads[s](inp)
                 eo = self.nets[s].enc(h)
                 enc_outs.append(eo)
                 inp = eo.F                                  # enc.feed_F
-        dec_F = [None] * self.scales
+        dec_F = [None] * len(forward_scales)
         prev = None
-        for s in reversed(range(self.scales)):
-            fuse = prev if (self._fuse_feat and s != self.scales - 1) else None
-            prev = self.nets[s].dec(enc_outs[s].bn_q, fuse, operand_only=(s == 0)).F
-            dec_F[s] = prev
-        for s in range(self.scales):
-            out.append(enc_outs[s], self.prob_clfs[s](dec_F[s]))
+        for i, s in reversed(list(enumerate(forward_scales))):
+            # no fusion for: disabled / auto-recursive scales / the final trained scale
+            fuse = prev if (self._fuse_feat and s != -1 and s != max(forward_scales)) else None
+            prev = self.nets[s].dec(enc_outs[i].bn_q, fuse, operand_only=(i == 0)).F
+            dec_F[i] = prev
+        for i, s in enumerate(forward_scales):
+            out.append(enc_outs[i], self.prob_clfs[s](dec_F[i]))
         return out
+
+    def sample_forward(self, x, losses, sample_scales, partial_final=None, auto_recurse=0):
+        """multiscale_network.py:328-406 (test.py --sample): encode x, then decode coarse -> fine, replacing
+        the bottlenecks of the scales in `sample_scales` (and always the image itself) by samples from the
+        predicted distributions; the coarsest sampled bottleneck is drawn uniformly.  Returns the sampled
+        image, NCHW float in [0, 255]."""
+        if auto_recurse != 0:
+            raise NotImplementedError('Currently not supported for sampling: autorecurse={}'.format(auto_recurse))
+        if self._rgb:
+            raise NotImplementedError('sampling is built for the L3C configurations (learned bottlenecks)')
+        print('-' * 40)
+        print('- Sampling {}'.format(sample_scales))
+        print('-' * 40)
+        img = self._as_u8_planes(x)
+        forward_scales = list(range(self.scales))
+        enc_outs, Cs = [], [3]
+        _, inp = E.rgb_prep(img, self.sub_rgb_mean, self.heads[0].head[0])
+        for s in forward_scales:
+            eo = self.nets[s].enc(self.heads[s](inp))
+            Cs.append(eo.S.shape[1])
+            enc_outs.append(eo)
+            inp = eo.F
+        prev_x, fuse = None, None
+        for scale in reversed(forward_scales):
+            loss_dmm = losses.loss_dmol_rgb if scale == 0 else losses.loss_dmol_n
+            C = Cs[scale]
+            if scale in sample_scales:
+                if prev_x is None:
+                    print('Sampling uniformly!')
+                    last = enc_outs[-1]
+                    n, c, h, w = last.S.shape
+                    fake = torch.empty(n, c, h, w, dtype=torch.float32, device=img.device).uniform_(-1, 1)
+                    prev_x = self.nets[-1].enc.quantize_x(fake)
+                    if partial_final:
+                        print('partial sampling')
+                        bnq = nchw_view(enc_outs[scale].bn_q, c)
+                        for ch in partial_final:
+                            prev_x[:, ch, ...] = bnq[:, ch, ...]
+                print('{}: Feeding sampled to decoder'.format(scale))
+                dec_in = to_nhwc(prev_x, 8)
+            else:
+                print('{}: Feeding encoder output to decoder'.format(scale))
+                dec_in = enc_outs[scale].bn_q
+            F = self.nets[scale].dec(dec_in, fuse, operand_only=(scale == 0)).F
+            if self._fuse_feat:
+                fuse = F
+            P = self.prob_clfs[scale](F)
+            if scale == 0 or scale - 1 in sample_scales:
+                print('{}: sampling N{}HW for next scale'.format(scale, C))
+                prev_x = loss_dmm.sample(nchw_view(P), C=C)
+        return prev_x
 
     def get_P_nhwc(self, scale, bn8, dec_F_prev=None, need_F=False):
         """-> (parameters NHWC, decoder features as engine.Act for the next finer scale).  At scale 0 the

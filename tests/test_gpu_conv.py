@@ -217,7 +217,7 @@ def test_f16_conv_vs_torch_on_fp16_operands(cout, rate, H, W, kw):
     assert torch.equal(plain, got.f)
     r_only = E.conv2d(cc, xa, precision=_lib.PREC_F16, want='round', residual=res, **kw)
     assert r_only.f is None and torch.equal(r_only.r, got.r)
-    if not kw.get('pixel_shuffle'):
+    if not kw.get('pixel_shuffle') and res is None:
         # channel-slice output into a wider FP16 buffer (the atrous concat): neighbours untouched
         buf = torch.full((3, H, W, 3 * cout), 7.0, dtype=torch.float16, device='cuda')
         E.conv2d(cc, xa, precision=_lib.PREC_F16, want='round', residual=res, out=buf, out_coff=cout, **kw)
@@ -261,16 +261,40 @@ def test_f16_conv_independent_of_batch_and_position():
 
 
 def test_ffma_writes_the_f16_image():
-    """CUDA-core layers (5x5/s2 down conv, Cin = 3 or 5) also produce the FP16 operand image in f16 mode."""
+    """CUDA-core layers (Cin = 3 or 5: RGB head, decoder head) also produce the FP16 operand image in f16 mode."""
     from l3c_pytorch_b200 import engine as E, _lib
-    conv = _conv_module(64, 64, 5, stride=2).cuda()
-    x = _nhwc(torch.randn(2, 64, 20, 36))
+    conv = _conv_module(5, 64, 1).cuda()
+    x = torch.zeros(2, 20, 36, 8, device='cuda')
+    x[..., :5] = torch.randn(2, 20, 36, 5, device='cuda')
+    fuse = torch.randn(2, 20, 36, 64, device='cuda')
     old = E.get_conv_precision()
     E.set_conv_precision('f16')
     try:
-        got = E.conv2d(conv, x, want='act')
+        got = E.conv2d(conv, x, residual=fuse, want='act')
     finally:
         E.set_conv_precision(old)
-    want = E.conv2d(conv, x, precision=FP32)
+    want = E.conv2d(conv, x, residual=fuse, precision=FP32)
     assert torch.equal(got.f, want)
     assert torch.equal(got.r, want.clamp(-65504.0, 65504.0).half())
+
+
+@pytest.mark.parametrize('H,W,kw', [(32, 48, {}), (18, 22, {}), (19, 37, dict(relu=True)), (64, 64, {}), (5, 7, {})])
+def test_f16_down_conv_5x5_stride2(H, W, kw):
+    """The encoders' 5x5 / stride-2 conv (net.py:101) on the tensor cores: TMA boxes with element strides
+    (2, 2) pick the input pixels of one filter tap; odd sizes, image borders (zero padding = TMA out-of-bounds
+    fill at negative and past-the-end coordinates)."""
+    from l3c_pytorch_b200 import engine as E, _lib
+    conv = _conv_module(64, 64, 5, stride=2)
+    x = torch.randn(3, 64, H, W)
+    want = F.conv2d(_h(x), _h(conv.weight.detach()), conv.bias.detach(), stride=2, padding=2)
+    if kw.get('relu'):
+        want = F.relu(want)
+    xa = E.Act(None, _nhwc(x).half())
+    got = E.conv2d(conv.cuda(), xa, precision=_lib.PREC_F16, want='act', **kw)
+    assert got.f.shape == (3, want.shape[2], want.shape[3], 64)
+    np.testing.assert_allclose(got.f.cpu().permute(0, 3, 1, 2).numpy(), want.numpy(), rtol=1e-4, atol=1e-4)
+    assert torch.equal(got.r.cpu(), got.f.cpu().half())
+    # batch / position independence (enc/dec bit-exactness is not needed for the encoder-only layer, but
+    # encode_batch(imgs[:1]) must give the same bytes as the first image of a bigger batch)
+    one = E.conv2d(conv.cuda(), E.Act(None, xa.r[1:2].contiguous()), precision=_lib.PREC_F16, want='plain', **kw)
+    assert torch.equal(one, got.f[1:2])

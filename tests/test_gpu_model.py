@@ -379,6 +379,35 @@ def test_async_encode_beside_a_decode_gives_the_same_bytes():
     assert jobs[1].finish()[0] == want_b and jobs[0].finish()[0] == datas_a
 
 
+def test_decodes_in_flight_on_two_lanes():
+    """Several decode_batch calls in flight, each on its own DecodeLane (the range decoders of all of them on
+    one SM partition), beside an encode on the side stream: every image comes back bit-exact and the
+    containers equal the synchronous ones."""
+    import l3c_pytorch_b200 as l3c
+    bp = util.blueprint('cr')
+    bc = l3c.Bitcoding(bp)
+    sets = [torch.stack([util.make_image(40 * k + i, 96, 160) for i in range(3)]) for k in range(4)]
+    datas = [bc.encode_batch(x)[0] for x in sets]
+    lanes = bc.decode_lanes(3, n_lanes=2)
+    assert len(lanes) == 2 and lanes[0].main.cuda_stream != lanes[1].main.cuda_stream
+    side = bc.side_stream(3, n_lanes=2)
+    cur = torch.cuda.current_stream()
+    job = bc.encode_batch_begin(sets[0].pin_memory(), stream=side)
+    outs = []
+    for k in range(4):                                        # four decodes queued on two lanes, none awaited
+        ln = lanes[k % 2]
+        ln.main.wait_stream(cur)
+        with torch.cuda.stream(ln.main):
+            outs.append(bc.decode_batch(datas[k], lane=ln))
+    assert job.finish()[0] == datas[0]
+    for ln in lanes:
+        cur.wait_stream(ln.main)
+    torch.cuda.synchronize()
+    for k in range(4):
+        for i in range(3):
+            assert torch.equal(outs[k][i][0].cpu(), sets[k][i].long()), (k, i)
+
+
 def test_sm_partition_streams_run_kernels_and_report_group_sizes():
     """l3c_partition_streams: two disjoint SM groups; a kernel launched into either gives the same
     result as on an ordinary stream.  Skipped where the driver has no green contexts."""
@@ -456,3 +485,80 @@ def test_part_files_are_not_overwritten(tmp_path, monkeypatch):
     open(q + '.part7', 'wb').close()                                  # a stale higher-numbered part
     with pytest.raises(AssertionError):
         bc.encode(img.long(), q)
+
+
+def test_recursive_theoretical_bpsp_matches_reference():
+    """`--recursive` evaluation of the RGB-shared baseline (the shared scale applied
+    again to its own thumbnails, multiscale_network.py:235-238,291-294) against per-scale costs of the
+    UNMODIFIED reference (tests/golden/recursive.json, oracle/gen_golden_recursive.py)."""
+    import json
+    from l3c_pytorch_b200 import engine as E
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'recursive.json')) as f:
+        cases = json.load(f)['cases']
+    bp = util.blueprint('cr_rgb_shared')
+    old = E.get_conv_precision()
+    E.set_conv_precision('fp32')
+    try:
+        for c in cases:
+            img = util.make_image(c['img_index'], c['H'], c['W']).unsqueeze(0).cuda()
+            out = bp.forward(img, auto_recurse=c['auto_recurse'])
+            assert [list(s.shape) for s in out.S] == c['S_shapes']
+            assert out.auto_recursive_from == 1
+            loss = bp.get_loss(out)
+            np.testing.assert_allclose(loss.nonrecursive_bpsps, c['nonrecursive_bpsps'], rtol=3e-4)
+            np.testing.assert_allclose(loss.recursive_bpsps, c['recursive_bpsps'], rtol=3e-4)
+            per_img = bp.get_loss_per_image(out)
+            assert abs(per_img[0] - sum(c['recursive_bpsps'])) < 3e-4 * sum(c['recursive_bpsps'])
+        # without recursion nothing changes
+        out0 = bp.forward(img)
+        assert out0.auto_recursive_from is None and bp.get_loss(out0).recursive_bpsps is None
+        # L3C proper: the flag is ignored by the tester (multiscale_tester.py:123-125) but the network supports it
+        bpl = util.blueprint('cr')
+        o = bpl.forward(util.make_image(0, 64, 64).unsqueeze(0).cuda(), auto_recurse=1)
+        assert len(o.S) == 5 and o.auto_recursive_from == 3
+    finally:
+        E.set_conv_precision(old)
+
+
+def test_sampling_kernel_and_sample_forward():
+    """`dmll_sample_kernel` against a plain PyTorch restatement of
+    logistic_mixture.py:277-323 fed with the SAME uniform random numbers, then the whole sample_forward
+    (multiscale_network.py:328-406) for the three styles test.py --sample writes."""
+    from l3c_pytorch_b200.dmll import DiscretizedMixLogisticLoss
+    g = torch.Generator().manual_seed(7)
+    for rgb, C, x_min, x_max, L in ((True, 3, 0, 255, 256), (False, 5, -1, 1, 25)):
+        K, N, H, W = 10, 2, 9, 13
+        P = 4 if rgb else 3
+        l = torch.randn(N, P * C * K, H, W, generator=g) * 1.5
+        lr = l.reshape(N, P, C, K, H, W)
+        if rgb:
+            lr[:, 1] = lr[:, 1] * 40 + 128
+            lr[:, 2] = lr[:, 2] + 1.5
+        u_sel = torch.empty(N, C, K, H, W).uniform_(1e-5, 1 - 1e-5, generator=g)
+        u_x = torch.empty(N, C, H, W).uniform_(1e-5, 1 - 1e-5, generator=g)
+        dm = DiscretizedMixLogisticLoss(rgb, x_min, x_max, L)
+        got = dm.sample(l.cuda(), C, u_sel.cuda(), u_x.cuda()).cpu()
+        sel = torch.argmax(lr[:, 0] - torch.log(-torch.log(u_sel)), dim=2).unsqueeze(2)
+        means = torch.gather(lr[:, 1], 2, sel).squeeze(2)
+        ls = torch.clamp(torch.gather(lr[:, 2], 2, sel).squeeze(2), min=-7.)
+        x = means + torch.exp(ls) * (torch.log(u_x) - torch.log(1. - u_x))
+        if rgb:
+            co = torch.sigmoid(lr[:, 3])
+            sg, sb = sel[:, 1], sel[:, 2]
+            c_gr = torch.gather(co[:, 0], 1, sg).squeeze(1)
+            c_br = torch.gather(co[:, 1], 1, sb).squeeze(1)
+            c_bg = torch.gather(co[:, 2], 1, sb).squeeze(1)
+            x0 = x[:, 0].clamp(0, 255.)
+            x1 = (x[:, 1] + c_gr * x0).clamp(0, 255.)
+            x2 = (x[:, 2] + c_br * x0 + c_bg * x1).clamp(0, 255.)
+            x = torch.stack((x0, x1, x2), dim=1)
+        assert got.shape == x.shape
+        np.testing.assert_allclose(got.numpy(), x.numpy(), rtol=2e-4, atol=2e-3)
+    bp = util.blueprint('cr')
+    img = util.make_image(0, 64, 96).unsqueeze(0).cuda()
+    for scales in ([], [0], [0, 1], [0, 1, 2]):
+        s = bp.sample_forward(img, scales)
+        assert s.shape == (1, 3, 64, 96) and s.dtype == torch.float32
+        assert float(s.min()) >= 0.0 and float(s.max()) <= 255.0 and bool(torch.isfinite(s).all())
+    s2 = bp.sample_forward(img, [0, 1, 2], partial_final=[0, 1])
+    assert s2.shape == (1, 3, 64, 96)

@@ -49,11 +49,11 @@ def test_harness_theory_and_write_to_files(tmp_path, capsys):
         assert abs(res.per_img[name] - want) <= 1e-5 * want, (name, res.per_img[name], want)
     # THEORETICAL cost of uint8 noise under default-init weights: ~39 bpsp (the reference itself reports
     # 36.4 + 2.3 + 0.6 + 0.1 at 32^2, tests/golden/summary.json `ref_theory_bpsps`: the cross-entropy is
-    # not floored at 16 bits per symbol the way the 16-bit coder is); c also pays for its padding
-    # (48*40 coded sub-pixels counted against 44*36)
+    # not floored at 16 bits per symbol the way the 16-bit coder is); c also pays for its zero padding
+    # (48*40 coded sub-pixels counted against 44*36) -- measured 40.0: zeros are far cheaper than noise
     for name in ('a', 'b'):
         assert 36.0 < res.per_img[name] < 43.0, (name, res.per_img[name])
-    assert 36.0 * (48 * 40) / (44 * 36) < res.per_img['c'] < 43.0 * (48 * 40) / (44 * 36), res.per_img['c']
+    assert 36.0 < res.per_img['c'] < 43.0 * (48 * 40) / (44 * 36), res.per_img['c']
 
     assert H.main([logs, '0306_0001', str(imgs), '--names', 'seed0']) == 0        # served from the cache
     out = capsys.readouterr().out

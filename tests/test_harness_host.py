@@ -112,9 +112,19 @@ class _FakeBlueprint(object):
         assert raw.dim() == 4 and raw.dtype == torch.uint8
         return raw.float(), raw.long()
 
-    def forward(self, img_batch):
+    def forward(self, img_batch, auto_recurse=0):
         self.batches.append(tuple(img_batch.shape))
+        self.recursions = getattr(self, 'recursions', []) + [auto_recurse]
         return img_batch
+
+    def get_loss(self, out):
+        class L(object):
+            nonrecursive_bpsps = [3.0, 1.0, 0.5, 0.25]
+        return L()
+
+    def sample_forward(self, img_batch, sample_scales, partial_final=None):
+        assert sample_scales in ([], [0], [0, 1])
+        return img_batch.float() * 0.5
 
     def get_loss_per_image(self, out, num_subpixels_before_pad=None):
         assert num_subpixels_before_pad == int(np.prod(out.shape[1:]))
@@ -166,6 +176,24 @@ def test_tester_control_flow_with_stand_ins(tree, capsys):
     txt = open(rep).read()
     assert txt.startswith('Average times:') and '=== bc.encode' in txt and '=== bc.decode' in txt
     assert '*** Summary:' not in capsys.readouterr().out
-    for argv2 in (argv + ['--recursive', 'auto'], argv + ['--sample', 's']):
-        with pytest.raises(NotImplementedError):
-            H.main(argv2, tester_cls=_fake_tester)
+    # --recursive: ignored for L3C proper (multiscale_tester.py:123-125), not combinable with --write_to_files
+    assert H.main(argv + ['--recursive', 'auto', '--overwrite_cache'], tester_cls=_fake_tester) == 0
+    assert set(_FakeBlueprint.made[-1].recursions) == {0}
+    # --sample: ground truth + three sampled images per test image, refuses to overwrite
+    sdir = str(tree['root'] / 'samples')
+    assert H.main(argv + ['--sample', sdir, '--overwrite_cache'], tester_cls=_fake_tester) == 0
+    names = sorted(os.listdir(os.path.join(sdir, '0306_0001')))
+    assert len(names) == 12 and sum(n.endswith('_gt.png') for n in names) == 3
+    assert any('_rgb+bn0+bn1_' in n for n in names) and any('_rgb_' in n for n in names)
+    with pytest.raises(FileExistsError):
+        H.main(argv + ['--sample', sdir, '--overwrite_cache'], tester_cls=_fake_tester)
+
+
+def test_recursive_flag():
+    """multiscale_tester.py:123-132"""
+    class C(object):
+        def __init__(self, rgb, n):
+            self.rgb_bicubic_baseline, self.num_scales = rgb, n
+    assert H.parse_recursive_flag('auto', C(False, 3)) == 0 and H.parse_recursive_flag('2', C(False, 3)) == 0
+    assert H.parse_recursive_flag('auto', C(True, 1)) == 3 and H.parse_recursive_flag('2', C(True, 1)) == 2
+    assert H.parse_recursive_flag('auto', C(True, 3)) == 0 and H.parse_recursive_flag('0', C(True, 1)) == 0
