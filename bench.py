@@ -476,6 +476,15 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1])
 
+    if args.value_only:                       # tuning sweeps: the device-resident figure only
+        if rank == 0:
+            print(json.dumps({'metric': METRIC, 'value': value, 'unit': 'Mpixels/s', 'ms_per_step': ms_total / args.steps,
+                              'steps': args.steps, 'lanes': args.lanes, 'precision': precision, 'value_only': True,
+                              'env': {k: v for k, v in os.environ.items() if k.startswith('L3C_')}}))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
     seq_value = seq_e2e = None
     if args.pipeline:
         seq_ms, _ = timed_sequential(lambda i: step_resident(dev_sets[i]))
@@ -704,6 +713,7 @@ def main():
                     help='conv mode (default: f16 = FP16-operand tensor cores for l3c/crops, fp32 for rgb_shared)')
     ap.add_argument('--images-per-gpu', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--value-only', action='store_true', help='tuning: print the device-resident value and stop')
     ap.add_argument('--lanes', type=int, default=int(os.environ.get('L3C_BENCH_LANES', 2)),
                     help='decodes in flight in the pipelined mode (default 2)')
     ap.add_argument('--no-pipeline', dest='pipeline', action='store_false',

@@ -211,6 +211,16 @@ typedef struct {
 
 int l3c_conv2d(const l3c_conv_t *p, void *stream);
 
+/* The DMLL head fused into the 1x1 `lin` conv of the probability classifier (encode side; reference:
+ * prob_clf.py:71-74 followed by logistic_mixture.py:248-275 and torchac_kernel.cu:26-76): the Kp parameters of
+ * a pixel never reach HBM -- the conv's epilogue evaluates the two CDF bounds of every coded symbol directly
+ * from the accumulator.  x_h: FP16 operand image NHWC [N][HW][Cin] (the atrous concat); w_h: FP16 weight image
+ * [Cin/64][cout_pad][64]; bias f32 [cout_pad]; sym_dev uint8 [N][C][HW]; targets_dev f32 [L+1];
+ * intervals_dev uint32 [N][C][HW] out, bit-identical to l3c_conv2d (F16) + l3c_dmll_intervals. */
+int l3c_lin_dmll_intervals(const void *x_h, const void *w_h, const float *bias, const uint8_t *sym_dev,
+                           const float *targets_dev, int N, int HW, int Cin, int C, int K, int L, int rgb,
+                           uint32_t *intervals_dev, void *stream);
+
 /* sub_rgb_mean + first MeanShift of RGBHead as one per-pixel 3x3 affine pair
  * (multiscale_network.py:181-183, head.py:31-33): img uint8 [N][3][HW] planes ->
  * x_sub f32 NHWC [N][HW][3] (= A1 img + b1)  and  t f32 NHWC [N][HW][4] (= A2 x_sub + b2, ch 3 = 0).

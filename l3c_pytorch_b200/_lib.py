@@ -58,6 +58,7 @@ _SIGNATURES = {
     'l3c_dmll_channel_params': (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p] * 4),
     'l3c_dmll_sample': (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p, c_void_p]),
     'l3c_conv2d': (c_int, [ctypes.POINTER(ConvDesc), c_void_p]),
+    'l3c_lin_dmll_intervals': (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p, c_void_p]),
     'l3c_rgb_prep': (c_int, [c_void_p] * 5 + [c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'l3c_quantize_head': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p, c_void_p, c_void_p]),
     'l3c_symbols_to_values': (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_void_p]),

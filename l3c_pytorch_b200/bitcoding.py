@@ -78,7 +78,10 @@ class Bitcoding(object):
         for (shape, pt), idxs in groups.items():
             batch = torch.cat([prepared[i][0] for i in idxs], 0)
             with self.times.run('[-] encode forwardpass'):
-                out = self.blueprint.forward(batch)
+                # without --compare_theory nobody reads the parameter tensors: the probability heads emit the
+                # coding intervals directly (f16 mode; MultiscaleNetwork.forward(intervals_of=...))
+                out = self.blueprint.forward(batch) if self.compare_with_theory else \
+                    self.blueprint.forward_for_coding(batch)
             if self.compare_with_theory:
                 with self.times.run('[-] get loss'):
                     loss_out = self.blueprint.get_loss(out)

@@ -37,6 +37,14 @@ class MultiscaleBlueprint(nn.Module):
         with torch.cuda.device(self.device):          # kernels launch on the CURRENT device
             return self.net(in_batch, auto_recurse)
 
+    def forward_for_coding(self, in_batch) -> Out:
+        """forward() for the bit-coder: in f16 mode the DMLL head is fused into the 1x1 convs of the probability
+        classifiers and `Out.IV` holds the coding intervals instead of `Out.P` the parameters."""
+        if self.device.type != 'cuda':
+            return self.net(in_batch, intervals_of=self.losses)
+        with torch.cuda.device(self.device):
+            return self.net(in_batch, intervals_of=self.losses)
+
     def get_loss(self, out: Out, num_subpixels_before_pad=None) -> MultiscaleLoss:
         """Theoretical bpsp per scale, incl. the uniform-prior final scale
         (multiscale_blueprint.py:64-95)."""

@@ -228,7 +228,7 @@ class BatchCodec(object):
         dev = imgs_u8.device
         N = imgs_u8.shape[0]
         if out is None:
-            out = self.net(imgs_u8)
+            out = self.net(imgs_u8, intervals_of=self.blueprint.losses)      # f16 mode: DMLL head fused into the convs
         K = self.net.config_ms.prob.K
 
         # ---- per-symbol intervals, scale by scale (coarse -> fine = container order)
@@ -239,6 +239,8 @@ class BatchCodec(object):
             shapes.append((scale, C, H, W))
             if uniform:
                 ivs.append(E.lut_intervals(S, self._uniform(dmll.L, dev)[0]))
+            elif out.IV is not None and out.IV[scale] is not None:
+                ivs.append(out.IV[scale])                                    # produced by the fused head
             else:
                 l = out.P_nhwc[scale]
                 assert non_shared_get_K(l.shape[-1], C) == K

@@ -37,6 +37,7 @@
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "dmll_math.cuh"
 
 namespace l3c {
 namespace f16 {
@@ -531,6 +532,211 @@ conv1x1_f16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The DMLL head fused into the 1x1 `lin` conv of the probability classifier (encode side): the GEMM of
+// conv1x1_f16_kernel, but the epilogue never writes the Kp parameters of a pixel (480 / 600 B) to HBM -- each
+// epilogue thread owns one pixel (TMEM lane), pulls the K logits / means / log-scales (and RGB coefficients) of
+// one channel at a time out of the accumulator, and evaluates the two CDF bounds of the symbol being coded
+// (dmll_math.cuh: the SAME functions the decoder's row builder uses on the parameters it computes with the
+// plain kernel, so both sides see identical integers).  Output: 4 B per coded sub-pixel.
+// Reference: criterion/logistic_mixture.py:248-275 + torchac_kernel.cu:26-76 after prob_clf.py:71-74.
+// ---------------------------------------------------------------------------------------------
+constexpr int LD_EPI_WARPS = 4;
+constexpr int LD_THREADS = 32 * (2 + LD_EPI_WARPS);
+
+struct ParamsLD {
+    const float *bias;
+    const uint8_t *sym;         // [N][C][HW] symbols being coded
+    const float *targets;       // [L + 1] bin edges
+    uint32_t *intervals;        // [N][C][HW] out
+    long long M;                // pixels = N * HW
+    int HW, L;
+    int kchunks, npad, tmem_cols;
+};
+
+__device__ __forceinline__ void tmem_ld10_issue(uint32_t taddr, float (&v)[10]) {
+    uint32_t r[10];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[8]), "=r"(r[9]) : "r"(taddr + 8u));
+#pragma unroll
+    for (int i = 0; i < 10; ++i) v[i] = __uint_as_float(r[i]);
+}
+// tcgen05.wait::ld tied to the registers it makes valid (the compiler must not use them earlier)
+__device__ __forceinline__ void tmem_ld10_wait(float (&v)[10]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                   "+f"(v[8]), "+f"(v[9])
+                 :
+                 : "memory");
+}
+
+template <int C, bool RGB>
+__global__ void __launch_bounds__(LD_THREADS, 1)
+lin_dmll_f16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                    const ParamsLD p, const int n_stages, const int n_tiles) {
+    constexpr int K = 10;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int w_bytes = p.kchunks * p.npad * 128;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + w_bytes + n_stages * K1_A_BYTES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * K1_MAX_STAGES + 5);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t w_base = smem_u32(smem);
+    const uint32_t a_base = w_base + w_bytes;
+    const uint32_t bar_base = smem_u32(bars);
+    const uint32_t full0 = bar_base, empty0 = bar_base + 8u * K1_MAX_STAGES;
+    const uint32_t tfull0 = bar_base + 8u * (2 * K1_MAX_STAGES), tempty0 = tfull0 + 16u;
+    const uint32_t wbar = tfull0 + 32u;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K1_MAX_STAGES; ++s) {
+            mbar_init(full0 + 8u * s, 1);
+            mbar_init(empty0 + 8u * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull0 + 8u * a, 1);
+            mbar_init(tempty0 + 8u * a, LD_EPI_WARPS);
+        }
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(wbar, (uint32_t)w_bytes);
+            for (int kc = 0; kc < p.kchunks; ++kc)
+                tma_load_2d(w_base + kc * p.npad * 128, &map_w, wbar, 0, kc * p.npad);
+        }
+        uint32_t stage = 0, phase = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                if (lane == 0) {
+                    mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+                    mbar_expect_tx(full0 + 8u * stage, K1_A_BYTES);
+                    tma_load_2d(a_base + stage * K1_A_BYTES, &map_x, full0 + 8u * stage, kc * 64, t * 128);
+                }
+                __syncwarp();
+                if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (warp-uniform code) =====================
+        const uint32_t idesc = idesc_f16((uint32_t)p.npad);
+        uint32_t stage = 0, phase = 0;
+        uint32_t acc = 0, acc_phase = 0;
+        mbar_wait(wbar, 0);
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.npad;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(full0 + 8u * stage, phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t da = make_desc(a_base + stage * K1_A_BYTES);
+                    const uint64_t db = make_desc(w_base + kc * p.npad * 128);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        mma_f16(d_tmem, da + 2u * kk, db + 2u * kk, idesc, (kc | kk) != 0 ? 1u : 0u);
+                    mma_commit(empty0 + 8u * stage);
+                    if (kc == p.kchunks - 1) mma_commit(tfull0 + 8u * acc);
+                }
+                __syncwarp();
+                if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1u; }
+            }
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    } else {
+        // ===================== epilogue: thread = pixel (TMEM lane 32*quarter + lane) =====================
+        const int quarter = warp & 3;
+        const float scale = (float)(65536 - p.L);            // 2^16 - (Lp - 1)
+        uint32_t acc = 0, acc_phase = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const long long pix = (long long)t * 128 + quarter * 32 + lane;
+            const bool valid = pix < p.M;
+            const int n = valid ? (int)(pix / p.HW) : 0;
+            const int q = valid ? (int)(pix % p.HW) : 0;
+            mbar_wait(tfull0 + 8u * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + acc * (uint32_t)p.npad + ((uint32_t)(quarter * 32) << 16);
+            float xr = 0.f, xg = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float logit[K], mean[K], logs[K], co0[K], co1[K];
+                tmem_ld10_issue(trow + 0 * C * K + c * K, logit);
+                tmem_ld10_issue(trow + 1 * C * K + c * K, mean);
+                tmem_ld10_issue(trow + 2 * C * K + c * K, logs);
+                if (RGB && c == 1) tmem_ld10_issue(trow + 3 * C * K + 0 * K, co0);
+                if (RGB && c == 2) {
+                    tmem_ld10_issue(trow + 3 * C * K + 1 * K, co0);
+                    tmem_ld10_issue(trow + 3 * C * K + 2 * K, co1);
+                }
+                tmem_ld10_wait(logit);
+                tmem_ld10_wait(mean);
+                tmem_ld10_wait(logs);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {                // + bias (same add as the plain kernel's epilogue)
+                    logit[k] += __ldg(p.bias + 0 * C * K + c * K + k);
+                    mean[k] += __ldg(p.bias + 1 * C * K + c * K + k);
+                    logs[k] += __ldg(p.bias + 2 * C * K + c * K + k);
+                }
+                if (RGB && c == 1) {
+                    tmem_ld10_wait(co0);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { co0[k] += __ldg(p.bias + 3 * C * K + 0 * K + k); co1[k] = 0.f; }
+                } else if (RGB && c == 2) {
+                    tmem_ld10_wait(co0);
+                    tmem_ld10_wait(co1);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        co0[k] += __ldg(p.bias + 3 * C * K + 1 * K + k);
+                        co1[k] += __ldg(p.bias + 3 * C * K + 2 * K + k);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) co0[k] = co1[k] = 0.f;
+                }
+                ChanParams<K> cp;
+                channel_params_core<K>(logit, mean, logs, co0, co1, c, RGB, xr, xg, cp);
+                const size_t so = ((size_t)n * C + c) * p.HW + q;
+                const int s = valid ? (int)p.sym[so] : 0;
+                const uint32_t lo = mixture_cdf_u16<K>(cp.pi, cp.mu, cp.inv_s, __ldg(p.targets + s), scale, s);
+                const uint32_t hi = (s == p.L - 1) ? 0x10000u
+                                                   : mixture_cdf_u16<K>(cp.pi, cp.mu, cp.inv_s, __ldg(p.targets + s + 1),
+                                                                        scale, s + 1);
+                if (valid) p.intervals[so] = lo | ((hi - 1u) << 16);
+                if (c == 0) xr = (float)s;
+                if (c == 1) xg = (float)s;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
 }  // namespace f16
 
 // operand image x_h: fp16 NHWC [N][H][W][x_pitch]; weight image w_h (engine.PackedConv.get_f16):
@@ -697,3 +903,68 @@ int conv2d_f16(const l3c_conv_t &p, cudaStream_t st) {
 }
 
 }  // namespace l3c
+
+// 1x1 conv (Cin % 64 == 0 -> Kp = (rgb ? 4 : 3) * C * 10 parameters) fused with the per-symbol coding intervals
+extern "C" int l3c_lin_dmll_intervals(const void *x_h, const void *w_h, const float *bias, const uint8_t *sym_dev,
+                                      const float *targets_dev, int N, int HW, int Cin, int C, int K, int L, int rgb,
+                                      uint32_t *intervals_dev, void *stream) {
+    using namespace l3c;
+    using namespace l3c::f16;
+    L3C_REQUIRE(x_h && w_h && bias && sym_dev && targets_dev && intervals_dev, "l3c_lin_dmll_intervals: null pointer");
+    L3C_REQUIRE(N >= 1 && HW >= 1 && Cin % 64 == 0 && Cin >= 64, "l3c_lin_dmll_intervals: N=%d HW=%d Cin=%d", N, HW, Cin);
+    L3C_REQUIRE(K == 10 && L >= 2 && L <= 256, "l3c_lin_dmll_intervals: K=%d L=%d (only K=10 is built)", K, L);
+    L3C_REQUIRE((rgb && C == 3) || (!rgb && C == 5), "l3c_lin_dmll_intervals: built for RGB (C=3) and C=5 bottlenecks, "
+                                                     "got C=%d rgb=%d", C, rgb);
+    const int Kp = (rgb ? 4 : 3) * C * K;
+    const int npad = (Kp + 63) / 64 * 64;
+    cudaStream_t st = (cudaStream_t)stream;
+    EncodeTiledFn encode = get_encode_fn();
+    L3C_REQUIRE(encode != nullptr, "l3c_lin_dmll_intervals: cuTensorMapEncodeTiled is not available from the driver");
+    static bool configured = false;
+    if (!configured) {
+        L3C_CUDA(cudaFuncSetAttribute(lin_dmll_f16_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        L3C_CUDA(cudaFuncSetAttribute(lin_dmll_f16_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    const int kchunks = Cin / 64;
+    const long long M = (long long)N * HW;
+    const int w_bytes = kchunks * npad * 128;
+    int n_stages = (227 * 1024 - 1024 - 512 - w_bytes) / K1_A_BYTES;
+    if (n_stages > K1_MAX_STAGES) n_stages = K1_MAX_STAGES;
+    L3C_REQUIRE(n_stages >= 2, "l3c_lin_dmll_intervals: weights do not fit in shared memory (Cin=%d)", Cin);
+    alignas(64) CUtensorMap map_x, map_w;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)M};
+        cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+        cuuint32_t box[2] = {64, 128};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(x_h), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        L3C_REQUIRE(r == CUDA_SUCCESS, "l3c_lin_dmll_intervals: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+    }
+    {
+        cuuint64_t dims[2] = {64, (cuuint64_t)kchunks * npad};
+        cuuint64_t strides[1] = {128};
+        cuuint32_t box[2] = {64, (cuuint32_t)npad};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(w_h), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        L3C_REQUIRE(r == CUDA_SUCCESS, "l3c_lin_dmll_intervals: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
+    }
+    ParamsLD q;
+    q.bias = bias; q.sym = sym_dev; q.targets = targets_dev; q.intervals = intervals_dev;
+    q.M = M; q.HW = HW; q.L = L; q.kchunks = kchunks; q.npad = npad;
+    q.tmem_cols = 2 * npad <= 128 ? 128 : (2 * npad <= 256 ? 256 : 512);
+    const int n_tiles = (int)((M + 127) / 128);
+    const int n_sm = stream_sm_count(st);
+    const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+    const int smem_bytes = w_bytes + n_stages * K1_A_BYTES + 1024 + 512;
+    if (rgb)
+        lin_dmll_f16_kernel<3, true><<<grid, LD_THREADS, smem_bytes, st>>>(map_x, map_w, q, n_stages, n_tiles);
+    else
+        lin_dmll_f16_kernel<5, false><<<grid, LD_THREADS, smem_bytes, st>>>(map_x, map_w, q, n_stages, n_tiles);
+    L3C_LAUNCH_CHECK("lin_dmll_f16_kernel");
+    return L3C_OK;
+}

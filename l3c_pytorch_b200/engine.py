@@ -462,6 +462,20 @@ def dmll_channel_params(l, x_dec, C, K, rgb, c):
     return outs
 
 
+def lin_dmll_intervals(conv, cat_h, sym, targets, C, K, L, rgb):
+    """1x1 `lin` conv of the probability classifier fused with the coding intervals (f16 mode, encode side):
+    cat_h FP16 NHWC [N,H,W,Cin] -> intervals uint32 (stored int32) [N,C,H*W]; the parameters never reach HBM."""
+    N, H, W, cin = cat_h.shape
+    assert cat_h.dtype == torch.float16 and cat_h.is_contiguous() and cin == conv.in_channels
+    assert conv.kernel_size[0] == 1 and conv.out_channels == (4 if rgb else 3) * C * K
+    w_h, b = _packed_obj(conv).get_f16()
+    iv = torch.empty(N, C, H * W, dtype=torch.int32, device=cat_h.device)
+    check(lib.l3c_lin_dmll_intervals(_ptr(cat_h), _ptr(w_h), _ptr(b), _ptr(sym), _ptr(targets), N, H * W, cin, C, K,
+                                     L, int(rgb), _ptr(iv), _stream_ptr()))
+    LAUNCHES['n'] += 1
+    return iv
+
+
 def dmll_sample(l, u_sel, u_x, C, K, rgb):
     """l NHWC [N,H,W,Kp]; u_sel f32 [N,C,K,H,W]; u_x f32 [N,C,H,W] -> sampled values f32 [N,C,H,W]."""
     N, H, W, _ = l.shape

@@ -238,8 +238,9 @@ class StackedAtrousConvs(nn.Module):
         self.atrous = nn.ModuleList([conv(Cin, Cin, kernel_size, rate=r) for r in rates])
         self.lin = conv(len(rates) * Cin, Cout, 1, bias=bias)
 
-    def forward(self, x):
-        """x: engine.Act -> NHWC parameter tensor."""
+    def forward(self, x, fused=None):
+        """x: engine.Act -> NHWC parameter tensor; or, with fused = (sym uint8 planes, dmll) in f16 mode, the
+        coding intervals of `sym` (the DMLL head runs in the 1x1 conv's epilogue: engine.lin_dmll_intervals)."""
         src = x.f if x.f is not None else x.r
         N, H, W, Cin = src.shape
         # f16 mode: the concat buffer IS the FP16 operand image of the 1x1 conv
@@ -249,6 +250,11 @@ class StackedAtrousConvs(nn.Module):
             # concat by channel slice; `cat` only feeds the 1x1 conv -> TF32-rounded in place when the
             # tensor cores are on
             E.conv2d(a, x, out=cat, out_coff=i * Cin, want='round')
+        if fused is not None:
+            sym, dm = fused
+            C = sym.shape[1]
+            return E.lin_dmll_intervals(self.lin, cat, sym, dm.targets(cat.device), C,
+                                        self.lin.out_channels // ((4 if dm.rgb_scale else 3) * C), dm.L, dm.rgb_scale)
         return E.conv2d(self.lin, E.Act(None, cat) if E.f16_mode() else cat)
 
 
@@ -259,8 +265,8 @@ class AtrousProbabilityClassifier(nn.Module):
         self.atrous = StackedAtrousConvs(atrous_rates_str, config_ms.Cf, non_shared_get_Kp(K, C),
                                          kernel_size=config_ms.kernel_size)
 
-    def forward(self, x):
-        return self.atrous(x)
+    def forward(self, x, fused=None):
+        return self.atrous(x, fused)
 
 
 class Out(object):
@@ -271,6 +277,7 @@ class Out(object):
     def __init__(self, targets_style='S', auto_recursive_from=None):
         assert targets_style in ('S', 'bn')
         self.S_u8, self.bn8, self.P_nhwc, self.L = [], [], [], []
+        self.IV = None          # per scale: coding intervals from the fused head (forward(intervals_of=...)), P is None then
         self.auto_recursive_from = auto_recursive_from
         self.targets_style = targets_style
 
@@ -379,8 +386,11 @@ class MultiscaleNetwork(nn.Module):
             x = x.round().clamp(0, 255).to(torch.uint8)
         return x.contiguous()
 
-    def forward(self, x, auto_recurse=0):
-        """x: image batch NCHW in [0,255] (uint8 / long / float).  Eval-mode forward
+    def forward(self, x, auto_recurse=0, intervals_of=None):
+        """intervals_of: a Losses object -> encode-side pass in f16 mode: the probability heads emit the coding
+        intervals of the symbols directly (Out.IV) and no parameter tensor is materialised (Out.P entries None).
+
+        x: image batch NCHW in [0,255] (uint8 / long / float).  Eval-mode forward
         (multiscale_network.py:226-306) -> Out.  auto_recurse: how many times the last trained scale is
         applied again (theoretical-bpsp evaluation of the RGB-shared baseline, `--recursive`;
         multiscale_network.py:235-238,291-294); the extra scales use scale index -1, never fuse decoder
@@ -411,7 +421,19 @@ class MultiscaleNetwork(nn.Module):
             fuse = prev if (self._fuse_feat and s != -1 and s != max(forward_scales)) else None
             prev = self.nets[s].dec(enc_outs[i].bn_q, fuse, operand_only=(i == 0)).F
             dec_F[i] = prev
+        fuse_iv = (intervals_of is not None and E.f16_mode() and not auto_recurse and
+                   all(self.prob_clfs[s].atrous.lin.in_channels % 64 == 0 for s in forward_scales))
+        if fuse_iv:
+            out.IV = []
         for i, s in enumerate(forward_scales):
+            if fuse_iv:
+                dm = intervals_of.loss_dmol_rgb if i == 0 else intervals_of.loss_dmol_n
+                C = out.S_u8[i].shape[1]
+                if (dm.rgb_scale and C == 3) or (not dm.rgb_scale and C == 5):
+                    out.IV.append(self.prob_clfs[s](dec_F[i], fused=(out.S_u8[i], dm)))
+                    out.append(enc_outs[i], None)
+                    continue
+                out.IV.append(None)
             out.append(enc_outs[i], self.prob_clfs[s](dec_F[i]))
         return out
 

@@ -298,3 +298,32 @@ def test_f16_down_conv_5x5_stride2(H, W, kw):
     # encode_batch(imgs[:1]) must give the same bytes as the first image of a bigger batch)
     one = E.conv2d(conv.cuda(), E.Act(None, xa.r[1:2].contiguous()), precision=_lib.PREC_F16, want='plain', **kw)
     assert torch.equal(one, got.f[1:2])
+
+
+@pytest.mark.parametrize('rgb,C,L,x_min,x_max,H,W', [(True, 3, 256, 0, 255, 24, 40), (False, 5, 25, -1, 1, 16, 16),
+                                                     (True, 3, 256, 0, 255, 7, 9)])
+def test_fused_lin_dmll_intervals_equal_the_two_step_path(rgb, C, L, x_min, x_max, H, W):
+    """The DMLL head fused into the 1x1 conv (l3c_lin_dmll_intervals) must give the SAME integers as the plain
+    F16 1x1 conv followed by l3c_dmll_intervals -- that is what the decoder's rows are built from."""
+    from l3c_pytorch_b200 import engine as E, _lib
+    from l3c_pytorch_b200.dmll import DiscretizedMixLogisticLoss
+    K = 10
+    Kp = (4 if rgb else 3) * C * K
+    conv = _conv_module(192, Kp, 1).cuda()
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        conv.weight.mul_(3.0)
+        if rgb:                                          # plausible means for 0..255 data
+            conv.bias[C * K:2 * C * K] = torch.rand(C * K, generator=g).cuda() * 255
+            conv.weight[C * K:2 * C * K] *= 20
+    cat = (torch.randn(2, H, W, 192, generator=g)).half().cuda()
+    sym = torch.randint(0, L, (2, C, H, W), generator=g, dtype=torch.uint8).cuda()
+    sym[0, :, 0, 0] = L - 1
+    sym[0, :, 0, 1] = 0
+    dm = DiscretizedMixLogisticLoss(rgb, x_min, x_max, L)
+    tg = dm.targets(cat.device)
+    l = E.conv2d(conv, E.Act(None, cat), precision=_lib.PREC_F16)
+    want = E.dmll_intervals(l, sym, tg, C, K, L, rgb)
+    got = E.lin_dmll_intervals(conv, cat, sym, tg, C, K, L, rgb)
+    assert got.shape == want.shape
+    assert torch.equal(got, want), int((got != want).sum())
