@@ -153,6 +153,17 @@ int l3c_dmll_build_table(const float *l_dev, const uint8_t *sym_dev, const float
                          int N, int HW, int C, int K, int L, int rgb, int c, int pix0, int npix,
                          uint16_t *table_dev, int pitch, void *stream);
 
+/* Tiled stream order (the codec's throughput mode): every H x W symbol plane is cut into tiles of th x tw
+ * (smaller at the right / bottom edge), tiles in row-major tile order, symbols row-major inside a tile; each
+ * tile is one coded stream.  l3c_dmll_build_table_tiled = l3c_dmll_build_table for ALL pixels with rows and
+ * sym_dev indexed in tile order (l_dev stays raster NHWC).  l3c_reorder_tiles converts `planes` planes of
+ * 1- or 4-byte elements between raster and tile order (to_tiles != 0: raster -> tiles). */
+int l3c_dmll_build_table_tiled(const float *l_dev, const uint8_t *sym_dev, const float *targets_dev,
+                               int N, int H, int W, int C, int K, int L, int rgb, int c, int th, int tw,
+                               uint16_t *table_dev, int pitch, void *stream);
+int l3c_reorder_tiles(const void *src_dev, void *dst_dev, int elem_bytes, int planes, int H, int W, int th,
+                      int tw, int to_tiles, void *stream);
+
 /* Negative log-likelihood (nats) summed per image: nll_dev f64 [N] (overwritten).
  * target value of symbol s is values_dev[s] (logistic_mixture.py:146-207). */
 int l3c_dmll_nll(const float *l_dev, const uint8_t *sym_dev, const float *values_dev,

@@ -54,6 +54,8 @@ _SIGNATURES = {
     'l3c_lut_intervals': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     'l3c_dmll_intervals': (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p, c_void_p]),
     'l3c_dmll_build_table': (c_int, [c_void_p] * 3 + [c_int] * 9 + [c_void_p, c_int, c_void_p]),
+    'l3c_dmll_build_table_tiled': (c_int, [c_void_p] * 3 + [c_int] * 10 + [c_void_p, c_int, c_void_p]),
+    'l3c_reorder_tiles': (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     'l3c_dmll_nll': (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_float, c_float, c_void_p, c_void_p, c_void_p]),
     'l3c_dmll_channel_params': (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p] * 4),
     'l3c_dmll_sample': (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p, c_void_p]),

@@ -23,10 +23,16 @@ _MAGIC_VALUE_SEP = MAGIC
 
 
 class Bitcoding(object):
-    def __init__(self, blueprint, times=NoOp, compare_with_theory=False):
+    def __init__(self, blueprint, times=NoOp, compare_with_theory=False, tile=None):
+        """tile = (th, tw): write TILED containers (codec.ContainerLayout): every channel plane of every scale is
+        cut into tiles coded as independent streams -- thousands of streams per batch instead of 18 per image,
+        so encode and decode are no longer bound by one warp's serial chain.  Not readable by the reference and a
+        few bytes per tile larger; decode() / decode_batch() recognise either layout.  Default: the reference's
+        byte-compatible `.l3c` layout."""
         self.blueprint = blueprint
         self.compare_with_theory = compare_with_theory
         self.times = times
+        self.tile = tile
         self.codec = BatchCodec(blueprint)
 
     # ------------------------------------------------------------------------------------------
@@ -86,7 +92,7 @@ class Bitcoding(object):
                 with self.times.run('[-] get loss'):
                     loss_out = self.blueprint.get_loss(out)
             with self.times.run('[-] entropy coding'):
-                datas, info = self.codec.encode_batch(batch, pt, out=out)
+                datas, info = self.codec.encode_batch(batch, pt, out=out, tile=self.tile)
             num_subpixels = int(np.prod(shape))
             for k, i in enumerate(idxs):
                 with open(pouts[i], 'wb') as f:
@@ -134,7 +140,7 @@ class Bitcoding(object):
             if any(pt):
                 x = torch.nn.functional.pad(x, pt, 'constant')
             x = x.contiguous()
-            job = self.codec.encode_begin(x, pt)
+            job = self.codec.encode_begin(x, pt, tile=self.tile)
         return _BatchEncodeJob(job, int(np.prod(x.shape[1:])))
 
     def side_stream(self, n_images, n_lanes=1):

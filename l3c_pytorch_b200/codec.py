@@ -65,23 +65,50 @@ def _slot_cap(n_sym):
     return ((n_sym * 17 + 7) // 8 + 64 + 3) & ~3
 
 
-class ContainerLayout(object):
-    """Byte layout of one container given its per-stream lengths (scale order coarse -> fine)."""
+TILED_MAGIC = b'L3CT'                # tiled containers: this tag + u16 tile_h + u16 tile_w follow the padding tuple
 
-    def __init__(self, shapes):
+
+def tile_grid(H, W, tile):
+    """[(offset, n_sym)] of the streams of one H x W symbol plane in stream order: the whole plane (compat
+    format) or its tiles of tile = (th, tw) in row-major tile order (tile-major symbol order, dmll.cu)."""
+    if tile is None:
+        return [(0, H * W)]
+    th, tw = tile
+    out, off = [], 0
+    for ty in range(-(-H // th)):
+        h = min(th, H - ty * th)
+        for tx in range(-(-W // tw)):
+            w = min(tw, W - tx * tw)
+            out.append((off, h * w))
+            off += h * w
+    return out
+
+
+class ContainerLayout(object):
+    """Byte layout of one container given its per-stream lengths (scale order coarse -> fine).
+    tile = None: the reference's `.l3c` layout (bitcoding.py:326-363), one stream per channel and scale.
+    tile = (th, tw): the throughput layout -- every channel plane is cut into tiles that are coded as
+    independent streams (thousands per batch instead of 18 per image); NOT readable by the reference and a few
+    bytes per tile larger (4-byte length + termination), reported by bench.py as `tiled`."""
+
+    def __init__(self, shapes, tile=None):
         self.shapes = shapes            # [(scale, C, H, W)] coarse -> fine
+        self.tile = tile
 
     def header_and_offsets(self, lens, pad_tuple):
         """lens: stream byte counts in container order.  Returns (total size, [(offset, bytes)]
         header pieces, [stream offsets])."""
         pieces = [(0, struct.pack('<4H', *pad_tuple))]
         pos = 8
+        if self.tile is not None:
+            pieces.append((pos, TILED_MAGIC + struct.pack('<HH', *self.tile)))
+            pos += 8
         offs = []
         i = 0
         for (_, C, H, W) in self.shapes:
             pieces.append((pos, struct.pack('<BHH', C, H, W)))
             pos += 5
-            for _ in range(C):
+            for _ in range(C * len(tile_grid(H, W, self.tile))):
                 n = int(lens[i])
                 pieces.append((pos, struct.pack('<I', n)))
                 pos += 4
@@ -93,13 +120,26 @@ class ContainerLayout(object):
         return pos, pieces, offs
 
 
+def container_tile(data):
+    """tile size (th, tw) of a tiled container, None for the reference layout."""
+    if len(data) >= 16 and bytes(data[8:12]) == TILED_MAGIC:
+        return struct.unpack_from('<HH', data, 12)
+    return None
+
+
 def parse_container(data):
-    """-> (pad_tuple, [(C, H, W, [(offset, length), ...])] coarse -> fine).  Raises ValueError on a
-    malformed file (the reference asserts on the magic, bitcoding.py:154)."""
+    """-> (pad_tuple, [(C, H, W, [(offset, length), ...])] coarse -> fine); tiled containers (container_tile)
+    list C * tiles streams per scale.  Raises ValueError on a malformed file (the reference asserts on the
+    magic, bitcoding.py:154)."""
     if len(data) < 8:
         raise ValueError('container too short')
     pad_tuple = struct.unpack_from('<4H', data, 0)
     pos = 8
+    tile = container_tile(data)
+    if tile is not None:
+        if tile[0] < 1 or tile[1] < 1:
+            raise ValueError('tiled container with an empty tile size')
+        pos = 16
     scales = []
     while pos < len(data):
         if pos + 5 > len(data):
@@ -107,7 +147,7 @@ def parse_container(data):
         C, H, W = struct.unpack_from('<BHH', data, pos)
         pos += 5
         streams = []
-        for _ in range(C):
+        for _ in range(C * len(tile_grid(H, W, tile))):
             if pos + 4 > len(data):
                 raise ValueError('truncated stream length')
             n, = struct.unpack_from('<I', data, pos)
@@ -142,7 +182,7 @@ class EncodeJob:
             raise RuntimeError('range coder output exceeded its slot (corrupt CDF?)')
         with torch.cuda.stream(self.stream):
             # ---- container layout + gather + single D2H
-            layout = ContainerLayout(shapes)
+            layout = ContainerLayout(shapes, self.tile)
             sizes, pieces_all, dst = [], [], np.zeros((N, per_img), np.int64)
             pos = 0
             starts = []
@@ -155,7 +195,8 @@ class EncodeJob:
                 pos += (total + 15) & ~15
             blob = torch.empty(pos + 16, dtype=torch.uint8, device=self.dev)
             E.pack_streams(self.desc_dev, self.lens_dev, dst.reshape(-1), N * per_img, blob)
-            info = dict(sizes=sizes, starts=starts, lens=lens, shapes=shapes, out=self.out, stream_offsets=dst)
+            info = dict(sizes=sizes, starts=starts, lens=lens, shapes=shapes, out=self.out, stream_offsets=dst,
+                        tile=self.tile)
             if not to_host:
                 self.packed = torch.cuda.Event()
                 self.packed.record(self.stream)
@@ -212,14 +253,15 @@ class BatchCodec(object):
         return self.net.nets[0].enc._consts(device)[1]
 
     # ------------------------------------------------------------------------------------------
-    def encode_batch(self, imgs_u8, pad_tuple=(0, 0, 0, 0), out=None, to_host=True):
+    def encode_batch(self, imgs_u8, pad_tuple=(0, 0, 0, 0), out=None, to_host=True, tile=None):
         """imgs_u8: uint8 [N,3,H,W] on the GPU, H and W multiples of 2**num_scales.
         Returns a list of N container byte strings (or, with to_host=False, the device blob,
-        per-image sizes and offsets, leaving the bytes in HBM).  `out`: a precomputed network Out."""
-        return self.encode_begin(imgs_u8, pad_tuple, out).finish(to_host)
+        per-image sizes and offsets, leaving the bytes in HBM).  `out`: a precomputed network Out.
+        tile = (th, tw): tiled containers (ContainerLayout)."""
+        return self.encode_begin(imgs_u8, pad_tuple, out, tile).finish(to_host)
 
     @_on_device
-    def encode_begin(self, imgs_u8, pad_tuple=(0, 0, 0, 0), out=None):
+    def encode_begin(self, imgs_u8, pad_tuple=(0, 0, 0, 0), out=None, tile=None):
         """First half of encode_batch: enqueues the whole GPU side of an encode (networks, intervals,
         the range-coder launch, the copy of the stream lengths to pinned memory) on the CURRENT stream
         and returns without waiting.  EncodeJob.finish() completes it.  Lets a caller overlap the
@@ -246,23 +288,29 @@ class BatchCodec(object):
                 assert non_shared_get_K(l.shape[-1], C) == K
                 ivs.append(E.dmll_intervals(l, S, dmll.targets(dev), C, K, dmll.L, dmll.rgb_scale))
 
-        # ---- one range-coder launch for all streams; descriptor order = (image, scale, channel)
-        per_img = sum(C for (_, C, _, _) in shapes)
-        caps = np.array([_slot_cap(H * W) for (_, C, H, W) in shapes for _ in range(C)], np.int64)
+        # ---- one range-coder launch for all streams; descriptor order = (image, scale, channel[, tile])
+        if tile is not None:
+            tile = (int(tile[0]), int(tile[1]))
+            # intervals are produced in raster order; the streams of a tiled container read them tile by tile
+            ivs = [E.reorder_tiles(iv, H, W, tile, True) for iv, (_, C, H, W) in zip(ivs, shapes)]
+        streams = [(si, c, off, n) for si, (_, C, H, W) in enumerate(shapes) for c in range(C)
+                   for (off, n) in tile_grid(H, W, tile)]
+        per_img = len(streams)
+        caps = np.array([_slot_cap(n) for (_, _, _, n) in streams], np.int64)
         slot_off = np.concatenate([[0], np.cumsum(caps)])
         img_slot_bytes = int(slot_off[-1])
         slots = torch.empty(N * img_slot_bytes, dtype=torch.uint8, device=dev)
         desc = np.zeros(N * per_img, dtype=_lib.ENC_STREAM_DTYPE)
         d = desc.reshape(N, per_img)
-        j = 0
-        for iv, (_, C, H, W) in zip(ivs, shapes):
-            base = iv.data_ptr()
-            for c in range(C):
-                d['intervals'][:, j] = base + (np.arange(N, dtype=np.int64) * C + c) * (H * W * 4)
-                d['n_sym'][:, j] = H * W
-                d['out_cap'][:, j] = caps[j]
-                d['out'][:, j] = slots.data_ptr() + np.arange(N, dtype=np.int64) * img_slot_bytes + slot_off[j]
-                j += 1
+        bases = np.array([iv.data_ptr() for iv in ivs], np.int64)
+        st = np.array(streams, np.int64)                                    # [per_img][4]
+        CHW = np.array([(C, H * W) for (_, C, H, W) in shapes], np.int64)[st[:, 0]]      # per stream: C, HW of its scale
+        img = np.arange(N, dtype=np.int64)[:, None]
+        d['intervals'][:] = bases[st[:, 0]][None, :] + ((img * CHW[None, :, 0] + st[None, :, 1]) * CHW[None, :, 1]
+                                                        + st[None, :, 2]) * 4
+        d['n_sym'][:] = st[None, :, 3]
+        d['out_cap'][:] = caps[None, :]
+        d['out'][:] = slots.data_ptr() + img * img_slot_bytes + slot_off[None, :-1]
         desc_dev, lens_dev = E.ac_encode_streams(desc, dev)
         lens_host = torch.empty(lens_dev.shape, dtype=lens_dev.dtype, pin_memory=True)
         lens_host.copy_(lens_dev, non_blocking=True)
@@ -271,7 +319,7 @@ class BatchCodec(object):
         job.coded = torch.cuda.Event()
         job.coded.record(job.stream)
         job.keep = (imgs_u8, ivs, slots)                       # alive until finish()
-        job.N, job.per_img, job.caps, job.shapes, job.out = N, per_img, caps, shapes, out
+        job.N, job.per_img, job.caps, job.shapes, job.out, job.tile = N, per_img, caps, shapes, out, tile
         job.pad_tuple, job.desc_dev, job.lens_dev, job.lens_host, job.dev = pad_tuple, desc_dev, lens_dev, lens_host, dev
         return job
 
@@ -284,8 +332,9 @@ class BatchCodec(object):
         N = len(datas)
         parsed = [parse_container(d) for d in datas]
         ref_shapes = [(C, H, W) for (C, H, W, _) in parsed[0][1]]
-        for p in parsed:
-            if [(C, H, W) for (C, H, W, _) in p[1]] != ref_shapes:
+        tile = container_tile(datas[0])
+        for p, dta in zip(parsed, datas):
+            if [(C, H, W) for (C, H, W, _) in p[1]] != ref_shapes or container_tile(dta) != tile:
                 raise ValueError('decode_batch needs containers of identical shape')
         # one upload of everything
         starts = np.zeros(N, np.int64)
@@ -301,7 +350,7 @@ class BatchCodec(object):
         offs = np.array([[starts[n] + o for (_, _, _, st) in parsed[n][1] for (o, _) in st] for n in range(N)],
                         np.int64)
         lens = np.array([[ln for (_, _, _, st) in parsed[n][1] for (_, ln) in st] for n in range(N)], np.int64)
-        S = self.decode_device(blob, offs, lens, ref_shapes, lane=lane)
+        S = self.decode_device(blob, offs, lens, ref_shapes, lane=lane, tile=tile)
         pads = [p[0] for p in parsed]
         if to_host:
             return S.cpu(), pads
@@ -430,13 +479,15 @@ class BatchCodec(object):
         return out
 
     @_on_device
-    def decode_device(self, blob, offs, lens, shapes, lane=None):
+    def decode_device(self, blob, offs, lens, shapes, lane=None, tile=None):
         """Decode streams that already sit in HBM: `blob` uint8 device buffer (readable 4 bytes past
         every stream), offs/lens int64 [N][streams per image] in container order (coarse -> fine,
         channel-major), shapes [(C,H,W)] coarse -> fine.  Returns uint8 [N,3,H,W] on the device.
         `lane` (self.lanes()): the stream set of this decode when several decodes are in flight; the caller
         has made `lane.main` the current stream.  Without it the range decoders of the bottleneck scales run
-        on the current stream and the RGB scale on lane 0 of a one-lane partition."""
+        on the current stream and the RGB scale on lane 0 of a one-lane partition.
+        `tile` = (th, tw): the streams are the tiles of a tiled container (ContainerLayout): thousands of short
+        streams, so the three RGB channels are simply decoded one after the other, all tiles at once."""
         dev = blob.device
         N = offs.shape[0]
         if len(shapes) != self.net.scales + 1:
@@ -446,17 +497,24 @@ class BatchCodec(object):
         bn8, F_prev, S = None, None, None
         j0 = 0
         self._mark('start')
+        if tile is not None:
+            tile = (int(tile[0]), int(tile[1]))
         for idx, (scale, dmll, uniform) in enumerate(self.iter_scale_dmll()):
             C, H, W = shapes[idx]
             HW = H * W
-            S = torch.empty(N, C, H, W, dtype=torch.uint8, device=dev)
-            desc = np.zeros(N * C, dtype=_lib.DEC_STREAM_DTYPE)
-            d = desc.reshape(N, C)
-            d['in'][:] = blob.data_ptr() + offs[:, j0:j0 + C]
-            d['in_len'][:] = lens[:, j0:j0 + C]
-            j0 += C
-            d['n_sym'][:] = HW
-            d['sym_out'][:] = S.data_ptr() + (np.arange(N)[:, None] * C + np.arange(C)[None, :]) * HW
+            S = torch.empty(N, C, H, W, dtype=torch.uint8, device=dev)      # symbols in STREAM order (tile order if tiled)
+            grid = tile_grid(H, W, tile)
+            T = len(grid)
+            g_off = np.array([o for (o, _) in grid], np.int64)[None, None, :]
+            g_n = np.array([n for (_, n) in grid], np.int64)[None, None, :]
+            desc = np.zeros(N * C * T, dtype=_lib.DEC_STREAM_DTYPE)
+            d = desc.reshape(N, C, T)
+            d['in'][:] = (blob.data_ptr() + offs[:, j0:j0 + C * T]).reshape(N, C, T)
+            d['in_len'][:] = lens[:, j0:j0 + C * T].reshape(N, C, T)
+            j0 += C * T
+            d['n_sym'][:] = g_n
+            plane = (np.arange(N)[:, None, None] * C + np.arange(C)[None, :, None]) * HW + g_off     # first symbol of the stream
+            d['sym_out'][:] = S.data_ptr() + plane
             pitch = E.table_pitch(dmll.L)
             if uniform:
                 row_dev = self._uniform(dmll.L, dev)[1]
@@ -470,15 +528,27 @@ class BatchCodec(object):
                     raise ValueError('container scale %d (%dx%dx%d) does not match the model output %s'
                                      % (scale, C, H, W, tuple(l.shape)))
                 table = torch.empty(N * C * HW * pitch, dtype=torch.int16, device=dev)
-                d['table'][:] = table.data_ptr() + \
-                    (np.arange(N)[:, None] * C + np.arange(C)[None, :]) * (HW * pitch * 2)
+                d['table'][:] = table.data_ptr() + plane * (pitch * 2)
                 d['row_pitch'][:] = pitch
                 tg = dmll.targets(dev)
-                if dmll.rgb_scale:
-                    self._decode_rgb_pipelined(l, S, tg, C, K, dmll.L, table, d, dev, lane=lane)
+                if tile is not None:
+                    if dmll.rgb_scale:
+                        # channel c's means depend on the decoded channels < c of the same pixel: R, G, B one
+                        # after the other, every tile of every image at once (N*T streams per launch)
+                        for c in range(C):
+                            E.dmll_build_table_tiled(l, S, tg, C, K, dmll.L, True, c, table, tile)
+                            dc = np.ascontiguousarray(d[:, c, :]).reshape(-1)
+                            self._on_decoder_stream(lane, lambda dc=dc: E.ac_decode_streams(dc, dev, dmll.L))
+                    else:
+                        E.dmll_build_table_tiled(l, S, tg, C, K, dmll.L, False, -1, table, tile)
+                        self._on_decoder_stream(lane, lambda: E.ac_decode_streams(desc, dev, dmll.L))
+                elif dmll.rgb_scale:
+                    self._decode_rgb_pipelined(l, S, tg, C, K, dmll.L, table, d.reshape(N, C), dev, lane=lane)
                 else:
                     E.dmll_build_table(l, S, tg, C, K, dmll.L, False, -1, table)
                     self._on_decoder_stream(lane, lambda: E.ac_decode_streams(desc, dev, dmll.L))
+            if tile is not None:
+                S = E.reorder_tiles(S, H, W, tile, False)                   # back to raster planes
             self._mark('uniform' if uniform else ('rgb' if dmll.rgb_scale and scale == 0 else 'S%d' % scale))
             if scale > 0:
                 bn8 = E.symbols_to_values(S, self._symbol_values(scale, dmll, dev), self._rgb_shift(dev))

@@ -440,6 +440,25 @@ def dmll_build_table(l, sym, targets, C, K, L, rgb, c, table, pix0=0, npix=None)
     LAUNCHES['n'] += 1
 
 
+def dmll_build_table_tiled(l, sym, targets, C, K, L, rgb, c, table, tile):
+    """rows of channel c (all channels for c < 0) in TILE order; `sym` (decoded channels) also in tile order."""
+    N, H, W, _ = l.shape
+    check(lib.l3c_dmll_build_table_tiled(_ptr(l), _ptr(sym), _ptr(targets), N, H, W, C, K, L, int(rgb), c,
+                                         tile[0], tile[1], _ptr(table), table_pitch(L), _stream_ptr()))
+    LAUNCHES['n'] += 1
+
+
+def reorder_tiles(src, H, W, tile, to_tiles):
+    """[planes..., H*W or H, W] uint8 / int32 tensor: raster <-> tile order (l3c_reorder_tiles); new tensor."""
+    assert src.is_contiguous() and src.dtype in (torch.uint8, torch.int32)
+    planes = src.numel() // (H * W)
+    dst = torch.empty_like(src)
+    check(lib.l3c_reorder_tiles(_ptr(src), _ptr(dst), src.element_size(), planes, H, W, tile[0], tile[1],
+                                1 if to_tiles else 0, _stream_ptr()))
+    LAUNCHES['n'] += 1
+    return dst
+
+
 def dmll_nll(l, sym, values, C, K, L, rgb, x_min, x_max, want_map=False):
     """-> (per-image nats float64 [N], per-sub-pixel nats f32 [N,C,H,W] or None)."""
     N, H, W, _ = l.shape

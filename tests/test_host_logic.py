@@ -261,3 +261,52 @@ def test_part_files_are_never_overwritten(tmp_path):
         open(p + psh.make_part_suffix(i), 'wb').close()
     open(p + '.partial', 'wb').close()                               # not a part file
     assert [psh.index_of_part_suffix(q) for q in psh.existing_parts(p)] == [0, 1, 2, 10]
+
+
+def test_tiled_container_layout_and_parser_round_trip():
+    """Tiled layout (codec.ContainerLayout with tile=(th, tw)): tile geometry incl. ragged edges, header tag,
+    parse_container recovers every stream; the reference layout is untouched."""
+    import struct
+    import numpy as np
+    from l3c_pytorch_b200 import codec as C
+
+    def order_to_raster(r, H, W, th, tw):          # Python restatement of dmll.cu: tile_order_to_raster
+        ty = r // (th * W)
+        h = min(th, H - ty * th)
+        rem = r - ty * th * W
+        tx = rem // (tw * h)
+        w = min(tw, W - tx * tw)
+        rem2 = rem - tx * tw * h
+        return (ty * th + rem2 // w) * W + tx * tw + rem2 % w
+
+    for (H, W, tile) in [(64, 96, (16, 16)), (37, 50, (16, 24)), (8, 8, (64, 64)), (5, 130, (2, 64))]:
+        grid = C.tile_grid(H, W, tile)
+        assert sum(n for (_, n) in grid) == H * W and grid[0][0] == 0
+        assert all(grid[i][0] + grid[i][1] == grid[i + 1][0] for i in range(len(grid) - 1))
+        seen = np.array([order_to_raster(r, H, W, *tile) for r in range(H * W)])
+        assert sorted(seen.tolist()) == list(range(H * W))                     # a permutation
+        # the first stream is the top-left tile, row-major inside
+        h0, w0 = min(tile[0], H), min(tile[1], W)
+        assert seen[:h0 * w0].tolist() == [y * W + x for y in range(h0) for x in range(w0)]
+    assert C.tile_grid(7, 9, None) == [(0, 63)]
+
+    shapes = [(3, 5, 8, 12), (2, 5, 16, 24), (1, 5, 32, 48), (0, 3, 64, 96)]
+    for tile in (None, (16, 16), (32, 40)):
+        layout = C.ContainerLayout(shapes, tile)
+        n_streams = sum(Cc * len(C.tile_grid(H, W, tile)) for (_, Cc, H, W) in shapes)
+        rng = np.random.default_rng(1)
+        lens = rng.integers(0, 40, n_streams)
+        total, pieces, offs = layout.header_and_offsets(lens, (1, 2, 3, 4))
+        buf = bytearray(total)
+        for (o, b) in pieces:
+            buf[o:o + len(b)] = b
+        for i, (o, n) in enumerate(zip(offs, lens)):
+            buf[o:o + n] = bytes([i % 251]) * int(n)
+        data = bytes(buf)
+        assert C.container_tile(data) == tile
+        pt, scales = C.parse_container(data)
+        assert pt == (1, 2, 3, 4) and [(c, h, w) for (c, h, w, _) in scales] == [(c, h, w) for (_, c, h, w) in shapes]
+        flat = [st for (_, _, _, sts) in scales for st in sts]
+        assert [o for (o, _) in flat] == list(offs) and [n for (_, n) in flat] == [int(x) for x in lens]
+        if tile is None:
+            assert data[8] == 5 and struct.unpack_from('<HH', data, 9) == (8, 12)      # reference layout untouched
