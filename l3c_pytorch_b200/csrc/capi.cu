@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "dmll_math.cuh"
 
 namespace l3c {
 
@@ -81,20 +82,18 @@ __global__ void repitch_kernel(const uint16_t *__restrict__ cdf, int64_t n_sym, 
     out[i] = (e < Lp - 1) ? cdf[r * Lp + e] : (uint16_t)0;
 }
 
-__device__ __forceinline__ float sigmoid_rn(float a) {
-    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-a)));
-}
-
-// cdf[n][l] of torchac_kernel.cu:58-75 with parameters given as [K][N] planes
+// cdf[n][l] of torchac_kernel.cu:58-75 with parameters given as [K][N] planes.  The arithmetic is the
+// library's single CDF function (dmll_math.cuh: mixture_cdf_u16 on -log2(e)/sigma), so a stream written through
+// this per-channel entry point equals the one the batched codec writes for the same parameters.
 __device__ __forceinline__ uint32_t plane_cdf_u16(const float *__restrict__ means,
                                                   const float *__restrict__ log_scales,
                                                   const float *__restrict__ probs, int K, int64_t N,
                                                   int64_t n, float target, float scale, int l) {
     float acc = 0.f;
     for (int k = 0; k < K; ++k) {
-        const float inv = expf(-log_scales[k * N + n]);
-        const float a = __fmul_rn(__fsub_rn(target, means[k * N + n]), inv);
-        acc = __fadd_rn(acc, __fmul_rn(probs[k * N + n], sigmoid_rn(a)));
+        const float is = __fmul_rn(expf(-log_scales[k * N + n]), NEG_LOG2E);
+        const float u = __fmul_rn(__fsub_rn(target, means[k * N + n]), is);
+        acc = __fmaf_rn(probs[k * N + n], sigmoid_from_log2(u), acc);
     }
     return (uint32_t)(__float2int_rn(__fmul_rn(acc, scale)) + l) & 0xFFFFu;
 }
