@@ -335,12 +335,22 @@ def run_ours(args):
         for ln in lanes:
             ln.main.wait_stream(cur)
         jobs = {}
+        tl = [] if dbg else None                      # timeline events (L3C_BENCH_DEBUG): where does a step go?
+
+        def tick(stream):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            return e
 
         def begin(i):
             if i < steps:
                 with torch.cuda.stream(side_stream):
+                    a = tick(side_stream) if dbg else None
                     jobs[i] = codec.encode_begin(dev_sets[(first_set + i) % n_sets], pad_tuple, tile=TILE['v'])
+                    if dbg:
+                        tl.append(('enc', i, a, tick(side_stream)))
 
+        t_origin = tick(cur) if dbg else None
         for i in range(ENC_DEPTH):
             begin(i)
         for s in range(steps):
@@ -353,14 +363,31 @@ def run_ours(args):
             with torch.cuda.stream(ln.main):
                 ln.main.wait_event(info['ready'])
                 blob.record_stream(ln.main)
+                a = tick(ln.main) if dbg else None
+                if dbg:
+                    codec.stage_events = []
                 S = codec.decode_device(blob, info['stream_offsets'], info['lens'], shapes_of(info), lane=ln,
                                         tile=TILE['v'])
+                if dbg:
+                    tl.append(('dec', s, a, tick(ln.main), codec.stage_events))
+                    codec.stage_events = None
             if dbg:
                 print('pipelined step %d: finish %.1f ms, begin(next) %.1f ms, decode issue %.1f ms'
                       % (s, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (time.perf_counter() - t2)), file=sys.stderr)
         for ln in lanes:
             cur.wait_stream(ln.main)              # ... and join it again
         cur.wait_stream(side_stream)
+        if dbg:
+            torch.cuda.synchronize()
+            for rec in sorted(tl, key=lambda r: (r[1], r[0] == 'dec')):
+                kind, i, a, b = rec[:4]
+                line = '  %s %2d: start %7.1f  end %7.1f  (%.1f ms)' % (kind, i, t_origin.elapsed_time(a),
+                                                                        t_origin.elapsed_time(b), a.elapsed_time(b))
+                if kind == 'dec':
+                    evs = rec[4]
+                    line += '  stages: ' + ' '.join('%s=%.1f' % (n2, e1.elapsed_time(e2))
+                                                     for (_, e1), (n2, e2) in zip(evs[:-1], evs[1:]))
+                print(line, file=sys.stderr)
         return S, info
 
     def run_e2e(steps, first_set=0):

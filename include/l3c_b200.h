@@ -239,6 +239,12 @@ int l3c_lin_dmll_intervals(const void *x_h, const void *w_h, const float *bias, 
 int l3c_rgb_prep(const uint8_t *img_dev, const float *A1, const float *b1, const float *A2,
                  const float *b2, int N, int HW, float *xsub_dev, float *t_dev, void *stream);
 
+/* F16 path of the RGB head (head.py:26-59): the two MeanShift affines of l3c_rgb_prep followed by an im2col of the
+ * 3x3 neighbourhood: out_h_dev FP16 [N][HW][64], element (ky*3+kx)*3 + c = normalised channel c at tap (ky,kx)
+ * (0 outside the image), elements 27..63 zero -- the 3 -> 64 conv then runs as a K = 64 GEMM on the tensor cores. */
+int l3c_rgb_im2col_f16(const uint8_t *img_dev, const float *A1, const float *b1, const float *A2, const float *b2,
+                       int N, int H, int W, void *out_h_dev, void *stream);
+
 /* to_q 1x1 conv + hard quantiser (net.py:116-148, quantizer.py:62-90):
  * sym = argmin_l (q - level_l)^2 (first minimum), bn_q = levels[sym].
  * f_dev NHWC [N][HW][Cf]; w_dev [Cf][C]; bias [C]; levels [L];

@@ -303,6 +303,58 @@ __global__ void rgb_prep_kernel(const uint8_t *__restrict__ img, const float *__
     }
 }
 
+// RGB head for the F16 tensor-core path: the two MeanShift affines (as rgb_prep_kernel) followed by an im2col of
+// the 3x3 neighbourhood -- per pixel one 128-byte row of 64 FP16 values, element tap*3 + c = normalised channel c
+// of the pixel at tap (ky, kx) (0 outside the image: the conv's zero padding acts on the NORMALISED input,
+// head.py:31-59), elements 27..63 zero.  The 3 -> 64 conv then is a 1x1 GEMM with K = 64 on the tensor cores
+// (conv1x1_f16_kernel) instead of 3.2 ms of CUDA-core work per 16 x 512^2 batch.
+__global__ void rgb_im2col_kernel(const uint8_t *__restrict__ img, const float *__restrict__ A1,
+                                  const float *__restrict__ b1, const float *__restrict__ A2,
+                                  const float *__restrict__ b2, int H, int W, uint4 *__restrict__ out) {
+    const int n = blockIdx.y;
+    const int HW = H * W;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int y0 = p / W, x0 = p % W;
+    float v[28];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y0 + tap / 3 - 1, xx = x0 + tap % 3 - 1;
+        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        float x[3], y[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[c] = in ? (float)img[((size_t)n * 3 + c) * HW + yy * W + xx] : 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) a = fmaf(A1[c * 3 + j], x[j], a);
+            y[c] = a + b1[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) a = fmaf(A2[c * 3 + j], y[j], a);
+            v[tap * 3 + c] = in ? a + b2[c] : 0.f;
+        }
+    }
+    v[27] = 0.f;
+    uint4 *dst = out + ((size_t)n * HW + p) * 8;            // 8 x 16 bytes
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = q * 8 + 2 * i;
+            w[i] = (e < 28) ? pack_h2(v[e], v[e + 1]) : 0u;
+        }
+        dst[q] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+#pragma unroll
+    for (int q = 4; q < 8; ++q) dst[q] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // to_q (1x1, Cf -> C) + hard quantiser.  One thread per pixel; C <= 8.
 constexpr int QMAXC = 8;
 __global__ void quantize_head_kernel(const float *__restrict__ f, const float *__restrict__ w,
@@ -380,6 +432,18 @@ extern "C" int l3c_rgb_prep(const uint8_t *img_dev, const float *A1, const float
     dim3 grid(ceil_div(HW, 256), N);
     rgb_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img_dev, A1, b1, A2, b2, HW, xsub_dev, t_dev);
     L3C_LAUNCH_CHECK("rgb_prep_kernel");
+    return L3C_OK;
+}
+
+extern "C" int l3c_rgb_im2col_f16(const uint8_t *img_dev, const float *A1, const float *b1, const float *A2,
+                                  const float *b2, int N, int H, int W, void *out_h_dev, void *stream) {
+    using namespace l3c;
+    L3C_REQUIRE(img_dev && A1 && b1 && A2 && b2 && out_h_dev && N >= 1 && H >= 1 && W >= 1 && N <= 65535,
+                "l3c_rgb_im2col_f16: bad arguments");
+    dim3 grid(ceil_div(H * W, 128), N);
+    rgb_im2col_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(img_dev, A1, b1, A2, b2, H, W,
+                                                              reinterpret_cast<uint4 *>(out_h_dev));
+    L3C_LAUNCH_CHECK("rgb_im2col_kernel");
     return L3C_OK;
 }
 

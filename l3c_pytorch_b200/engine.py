@@ -103,6 +103,7 @@ class PackedConv(object):
             self.w, self.b, self._key = wp, bp, key
             self.w_tc = None
             self.w_h = None
+            self.w_im2col = None
         return self.w, self.b
 
     def get_tc(self):
@@ -365,6 +366,40 @@ def rgb_prep(img_u8, conv1, conv2):
                            _ptr(xsub), _ptr(t), _stream_ptr()))
     LAUNCHES['n'] += 1
     return xsub, t
+
+
+def rgb_head_f16(img_u8, conv1, conv2, head_conv):
+    """f16 mode: RGBHead (the two MeanShift affines + conv 3 -> Cf, 3x3) on the tensor cores: im2col of the
+    normalised 3x3 neighbourhood (l3c_rgb_im2col_f16) + a K = 64 GEMM (conv1x1_f16_kernel).  -> Act carrying only
+    the FP16 operand image of the head output (it feeds nothing but the encoder's down-sampling conv)."""
+    require_cuda(img_u8, 'img')
+    assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous()
+    N, _, H, W = img_u8.shape
+    A1 = conv1.weight.detach().float().reshape(9).contiguous()
+    b1 = conv1.bias.detach().float().contiguous()
+    A2 = conv2.weight.detach().float().reshape(9).contiguous()
+    b2 = conv2.bias.detach().float().contiguous()
+    cols = torch.empty(N, H, W, 64, dtype=torch.float16, device=img_u8.device)
+    check(lib.l3c_rgb_im2col_f16(_ptr(img_u8), _ptr(A1), _ptr(b1), _ptr(A2), _ptr(b2), N, H, W, _ptr(cols),
+                                 _stream_ptr()))
+    LAUNCHES['n'] += 1
+    pc = _packed_obj(head_conv)
+    _, b = pc.get()
+    if getattr(pc, 'w_im2col', None) is None:
+        w = head_conv.weight.detach().float().clamp(-65504.0, 65504.0)        # [Cf, 3, 3, 3]
+        cout = w.shape[0]
+        assert tuple(w.shape[1:]) == (3, 3, 3) and cout % 2 == 0 and b.shape[0] <= 256
+        img = torch.zeros(1, b.shape[0], 64, dtype=torch.float16, device=w.device)
+        img[0, :cout, :27] = w.permute(0, 2, 3, 1).reshape(cout, 27).half()   # k = (ky*3 + kx)*3 + c
+        pc.w_im2col = img.contiguous()
+    cout = head_conv.out_channels
+    y_h = torch.empty(N, H, W, cout, dtype=torch.float16, device=img_u8.device)
+    d = ConvDesc(x_h=cols.data_ptr(), w_h=pc.w_im2col.data_ptr(), bias=b.data_ptr(), y_h=y_h.data_ptr(),
+                 N=N, H=H, W=W, Cin=64, x_pitch=64, Cout=cout, cout_pad=b.shape[0], y_pitch=cout, y_coff=0,
+                 ksize=1, stride=1, dilation=1, flags=0, precision=_lib.PREC_F16)
+    check(lib.l3c_conv2d(ctypes.byref(d), _stream_ptr()))
+    LAUNCHES['n'] += 1
+    return Act(None, y_h)
 
 
 def quantize_head(f, to_q_conv, levels):

@@ -386,6 +386,14 @@ class MultiscaleNetwork(nn.Module):
             x = x.round().clamp(0, 255).to(torch.uint8)
         return x.contiguous()
 
+    def _rgb_head_input(self, img):
+        """What feeds the first encoder: in f16 mode the OUTPUT of heads[0] (MeanShift x2 + 3 -> Cf conv, computed as
+        im2col + tensor-core GEMM, engine.rgb_head_f16) as an engine.Act; otherwise the normalised image for
+        heads[0] to convolve on the CUDA cores."""
+        if E.f16_mode() and self.heads[0].head[1].head.out_channels % 2 == 0:
+            return E.rgb_head_f16(img, self.sub_rgb_mean, self.heads[0].head[0], self.heads[0].head[1].head)
+        return E.rgb_prep(img, self.sub_rgb_mean, self.heads[0].head[0])[1]
+
     def forward(self, x, auto_recurse=0, intervals_of=None):
         """intervals_of: a Losses object -> encode-side pass in f16 mode: the probability heads emit the coding
         intervals of the symbols directly (Out.IV) and no parameter tensor is materialised (Out.P entries None).
@@ -408,9 +416,9 @@ class MultiscaleNetwork(nn.Module):
                 enc_outs.append(eo)
                 inp = eo.S
         else:
-            _, inp = E.rgb_prep(img, self.sub_rgb_mean, self.heads[0].head[0])
-            for s in forward_scales:
-                h = self.heads[s](inp)
+            inp = self._rgb_head_input(img)
+            for i, s in enumerate(forward_scales):
+                h = inp if (i == 0 and isinstance(inp, E.Act)) else self.heads[s](inp)
                 eo = self.nets[s].enc(h)
                 enc_outs.append(eo)
                 inp = eo.F                                  # enc.feed_F
@@ -452,9 +460,9 @@ class MultiscaleNetwork(nn.Module):
         img = self._as_u8_planes(x)
         forward_scales = list(range(self.scales))
         enc_outs, Cs = [], [3]
-        _, inp = E.rgb_prep(img, self.sub_rgb_mean, self.heads[0].head[0])
-        for s in forward_scales:
-            eo = self.nets[s].enc(self.heads[s](inp))
+        inp = self._rgb_head_input(img)
+        for i, s in enumerate(forward_scales):
+            eo = self.nets[s].enc(inp if (i == 0 and isinstance(inp, E.Act)) else self.heads[s](inp))
             Cs.append(eo.S.shape[1])
             enc_outs.append(eo)
             inp = eo.F

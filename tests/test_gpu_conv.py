@@ -327,3 +327,23 @@ def test_fused_lin_dmll_intervals_equal_the_two_step_path(rgb, C, L, x_min, x_ma
     got = E.lin_dmll_intervals(conv, cat, sym, tg, C, K, L, rgb)
     assert got.shape == want.shape
     assert torch.equal(got, want), int((got != want).sum())
+
+
+@pytest.mark.parametrize('H,W', [(32, 48), (17, 23), (64, 64)])
+def test_rgb_head_im2col_gemm(H, W):
+    """f16 mode: RGBHead (MeanShift x2 + conv 3 -> 64, 3x3, zero padding of the NORMALISED input) as im2col + a
+    K = 64 tensor-core GEMM, against PyTorch on the same FP16-rounded operands."""
+    from l3c_pytorch_b200 import engine as E
+    bp = util.blueprint('cr')
+    net = bp.net
+    img = torch.stack([util.make_image(i, H, W) for i in range(2)])
+    got = E.rgb_head_f16(img.cuda(), net.sub_rgb_mean, net.heads[0].head[0], net.heads[0].head[1].head)
+    assert got.f is None and got.r.shape == (2, H, W, 64) and got.r.dtype == torch.float16
+    x = img.float()
+    m1, m2, hc = net.sub_rgb_mean.cpu(), net.heads[0].head[0].cpu(), net.heads[0].head[1].head.cpu()
+    try:
+        z = m2(m1(x)).detach()
+        want = F.conv2d(_h(z), _h(hc.weight.detach()), hc.bias.detach(), padding=1)
+    finally:
+        net.cuda()
+    np.testing.assert_allclose(got.r.float().cpu().permute(0, 3, 1, 2).numpy(), want.numpy(), rtol=2e-3, atol=2e-3)
