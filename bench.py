@@ -25,6 +25,10 @@ import sys
 import threading
 import time
 
+# several decodes in flight = dozens of streams full of event-dependent launches: give them their own hardware
+# queues (default 8: a ready kernel waits behind another decode's queued, not-yet-ready ones)
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -321,7 +325,8 @@ def run_ours(args):
     # args.lanes decodes are in flight at any time (each on its own set of streams; the range decoders of all
     # of them share one group of SMs), and two encodes are queued ahead on the lowest-priority stream.
     n_lanes = max(1, args.lanes)
-    lanes, side_stream = codec.lanes(dev, 3 * n_units, n_lanes) if args.pipeline else (None, None)
+    lanes, side_stream = codec.lanes(dev, 3 * n_units, n_lanes)[:2] if args.pipeline else (None, None)
+    enc_streams = codec.encode_streams(dev, 3 * n_units, n_lanes) if args.pipeline else None
     ENC_DEPTH = 2
 
     def run_resident(steps, first_set=0):
@@ -331,7 +336,8 @@ def run_ours(args):
             return S, info
         dbg = os.environ.get('L3C_BENCH_DEBUG')
         cur = torch.cuda.current_stream()
-        side_stream.wait_stream(cur)              # the timing events live on `cur`: fork from it ...
+        for es in enc_streams:
+            es.wait_stream(cur)                   # the timing events live on `cur`: fork from it ...
         for ln in lanes:
             ln.main.wait_stream(cur)
         jobs = {}
@@ -344,11 +350,12 @@ def run_ours(args):
 
         def begin(i):
             if i < steps:
-                with torch.cuda.stream(side_stream):
-                    a = tick(side_stream) if dbg else None
+                es = enc_streams[i % len(enc_streams)]     # alternate: the latency-bound range-encoder launch of
+                with torch.cuda.stream(es):                # batch i overlaps the convs of batch i+1
+                    a = tick(es) if dbg else None
                     jobs[i] = codec.encode_begin(dev_sets[(first_set + i) % n_sets], pad_tuple, tile=TILE['v'])
                     if dbg:
-                        tl.append(('enc', i, a, tick(side_stream)))
+                        tl.append(('enc', i, a, tick(es)))
 
         t_origin = tick(cur) if dbg else None
         for i in range(ENC_DEPTH):
@@ -376,7 +383,8 @@ def run_ours(args):
                       % (s, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (time.perf_counter() - t2)), file=sys.stderr)
         for ln in lanes:
             cur.wait_stream(ln.main)              # ... and join it again
-        cur.wait_stream(side_stream)
+        for es in enc_streams:
+            cur.wait_stream(es)
         if dbg:
             torch.cuda.synchronize()
             for rec in sorted(tl, key=lambda r: (r[1], r[0] == 'dec')):
@@ -396,14 +404,16 @@ def run_ours(args):
                 back, datas = step_e2e((first_set + s) % n_sets)
             return back, datas
         cur = torch.cuda.current_stream()
-        side_stream.wait_stream(cur)
+        for es in enc_streams:
+            es.wait_stream(cur)
         for ln in lanes:
             ln.main.wait_stream(cur)
         jobs = {}
 
         def begin(i):
             if i < steps:
-                jobs[i] = bc.encode_batch_begin(host_sets[(first_set + i) % n_sets], stream=side_stream)
+                jobs[i] = bc.encode_batch_begin(host_sets[(first_set + i) % n_sets],
+                                                stream=enc_streams[i % len(enc_streams)])
 
         for i in range(ENC_DEPTH):
             begin(i)
@@ -428,7 +438,8 @@ def run_ours(args):
         back = bufs[(steps - 1) % (n_lanes + 1)]
         for ln in lanes:
             cur.wait_stream(ln.main)
-        cur.wait_stream(side_stream)
+        for es in enc_streams:
+            cur.wait_stream(es)
         return back, datas
 
     def check_lossless(S, k, what):

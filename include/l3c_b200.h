@@ -278,6 +278,9 @@ int l3c_bicubic_half_u8(const uint8_t *in_dev, int N, int H, int W, uint8_t *out
  * uses ordinary streams (slower, same results). */
 int l3c_partition_streams(int sm_a, int n_a, void **streams_a, int n_b, void **streams_b,
                           int *sm_a_out, int *sm_b_out);
+/* the same with explicit counts of high- and default-priority streams on the remaining SMs */
+int l3c_partition_streams2(int sm_a, int n_a, void **streams_a, int n_b_high, void **streams_b_high,
+                           int n_b_low, void **streams_b_low, int *sm_a_out, int *sm_b_out);
 
 #ifdef __cplusplus
 }

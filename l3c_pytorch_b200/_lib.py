@@ -68,6 +68,7 @@ _SIGNATURES = {
     'l3c_bicubic_half_u8': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'l3c_pack_streams': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     'l3c_partition_streams': (c_int, [c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    'l3c_partition_streams2': (c_int, [c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 EXPORTS = sorted(_SIGNATURES)

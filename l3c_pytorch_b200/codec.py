@@ -442,7 +442,7 @@ class BatchCodec(object):
                 want = -(-(2 * n_decoders * n_lanes) // (8 * wps)) * 8
                 want = min(max(8, want), (n_sm // 16) * 8)
                 want = int(os.environ.get('L3C_DEC_SMS', want))           # bring-up knob
-                part = E.partition_streams(dev, want, 3 * n_lanes, 4 * n_lanes + 1)
+                part = E.partition_streams2(dev, want, 3 * n_lanes, 4 * n_lanes, 2)
             lanes = []
             for i in range(n_lanes):
                 ln = DecodeLane()
@@ -458,9 +458,15 @@ class BatchCodec(object):
                     ln.main = torch.cuda.Stream(device=dev, priority=-1)
                     ln.partitioned = False
                 lanes.append(ln)
-            enc = part[1][4 * n_lanes] if part is not None else torch.cuda.Stream(device=dev)
-            cache[key] = (lanes, enc)
+            # two encode streams (default priority): the range-encoder launch of one batch is latency-bound (one
+            # warp per stream, ~16 ms) and overlaps the convs of the next batch when they alternate
+            encs = part[2] if part is not None else [torch.cuda.Stream(device=dev) for _ in range(2)]
+            cache[key] = (lanes, encs[0], encs)
         return cache[key]
+
+    def encode_streams(self, dev, n_decoders, n_lanes=1):
+        """The two default-priority streams for encodes that run beside decodes (alternate between them)."""
+        return self.lanes(dev, n_decoders, n_lanes)[2]
 
     def _on_decoder_stream(self, lane, fn):
         """Run the launches of `fn` on the lane's first decoder stream (the decoders' SM group), ordered

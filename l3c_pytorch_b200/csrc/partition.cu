@@ -85,9 +85,21 @@ int stream_sm_count(cudaStream_t st) {
 
 }  // namespace l3c
 
+extern "C" int l3c_partition_streams2(int sm_a, int n_a, void **streams_a, int n_b_high, void **streams_b_high,
+                                      int n_b_low, void **streams_b_low, int *sm_a_out, int *sm_b_out);
+
 extern "C" int l3c_partition_streams(int sm_a, int n_a, void **streams_a, int n_b, void **streams_b,
                                      int *sm_a_out, int *sm_b_out) {
+    // all but the last stream of group B are high priority, the last one has default priority
+    return l3c_partition_streams2(sm_a, n_a, streams_a, n_b > 0 ? n_b - 1 : 0, streams_b, n_b > 0 ? 1 : 0,
+                                  n_b > 0 ? streams_b + (n_b - 1) : nullptr, sm_a_out, sm_b_out);
+}
+
+extern "C" int l3c_partition_streams2(int sm_a, int n_a, void **streams_a, int n_b, void **streams_b,
+                                      int n_b_low, void **streams_b_low, int *sm_a_out, int *sm_b_out) {
     using namespace l3c;
+    L3C_REQUIRE(n_b_low >= 0 && n_b_low <= 64 && (n_b_low == 0 || streams_b_low), "l3c_partition_streams2: bad arguments");
+
     L3C_REQUIRE(sm_a > 0 && n_a >= 0 && n_b >= 0 && n_a <= 64 && n_b <= 64 && (n_a == 0 || streams_a) &&
                     (n_b == 0 || streams_b),
                 "l3c_partition_streams: bad arguments");
@@ -144,14 +156,14 @@ extern "C" int l3c_partition_streams(int sm_a, int n_a, void **streams_a, int n_
         }
         return true;
     };
-    if (!grow(part->streams_a, part->ctx_a, n_a, -1) || !grow(part->streams_b, part->ctx_b, n_b - 1, -1) ||
-        !grow(part->streams_b_low, part->ctx_b, n_b > 0 ? 1 : 0, 0)) {
+    if (!grow(part->streams_a, part->ctx_a, n_a, -1) || !grow(part->streams_b, part->ctx_b, n_b, -1) ||
+        !grow(part->streams_b_low, part->ctx_b, n_b_low, 0)) {
         set_error("l3c_partition_streams: could not create / use a partition stream on device %d", dev);
         return L3C_EUNSUPPORTED;
     }
     for (int i = 0; i < n_a; ++i) streams_a[i] = (void *)part->streams_a[i];
-    for (int i = 0; i + 1 < n_b; ++i) streams_b[i] = (void *)part->streams_b[i];
-    if (n_b > 0) streams_b[n_b - 1] = (void *)part->streams_b_low[0];
+    for (int i = 0; i < n_b; ++i) streams_b[i] = (void *)part->streams_b[i];
+    for (int i = 0; i < n_b_low; ++i) streams_b_low[i] = (void *)part->streams_b_low[i];
     if (sm_a_out) *sm_a_out = part->sm_a;
     if (sm_b_out) *sm_b_out = part->sm_b;
     return L3C_OK;

@@ -72,6 +72,27 @@ def partition_streams(device, sm_a, n_a, n_b):
     return _PARTITIONS[key]
 
 
+def partition_streams2(device, sm_a, n_a, n_b_high, n_b_low):
+    """l3c_partition_streams2: -> (streams_a, streams_b_high, streams_b_low, sm_a, sm_b) or None."""
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), sm_a, n_a, n_b_high, n_b_low, 'v2')
+    if key not in _PARTITIONS:
+        a = (ctypes.c_void_p * max(1, n_a))()
+        bh = (ctypes.c_void_p * max(1, n_b_high))()
+        bl = (ctypes.c_void_p * max(1, n_b_low))()
+        got_a, got_b = ctypes.c_int(0), ctypes.c_int(0)
+        with torch.cuda.device(key[0]):
+            rc = lib.l3c_partition_streams2(sm_a, n_a, a, n_b_high, bh, n_b_low, bl, ctypes.byref(got_a),
+                                            ctypes.byref(got_b))
+        if rc == _lib.E_UNSUPPORTED:
+            _PARTITIONS[key] = None
+        else:
+            check(rc)
+            mk = lambda arr, n: [torch.cuda.ExternalStream(int(arr[i]), device=key[0]) for i in range(n)]
+            _PARTITIONS[key] = (mk(a, n_a), mk(bh, n_b_high), mk(bl, n_b_low), got_a.value, got_b.value)
+    return _PARTITIONS[key]
+
+
 def require_cuda(t, name):
     if not t.is_cuda:
         raise ValueError('%s must be a CUDA tensor (l3c_pytorch_b200 has no CPU path)' % name)
