@@ -327,7 +327,7 @@ def run_ours(args):
     n_lanes = max(1, args.lanes)
     lanes, side_stream = codec.lanes(dev, 3 * n_units, n_lanes)[:2] if args.pipeline else (None, None)
     enc_streams = codec.encode_streams(dev, 3 * n_units, n_lanes) if args.pipeline else None
-    ENC_DEPTH = 2
+    ENC_DEPTH = int(os.environ.get('L3C_BENCH_ENC_DEPTH', 2))
 
     def run_resident(steps, first_set=0):
         if not args.pipeline:
@@ -790,8 +790,8 @@ def main():
     ap.add_argument('--tile', type=int, nargs=2, default=None, metavar=('TH', 'TW'),
                     help='run the whole bench on TILED containers (throughput layout, not reference-compatible)')
     ap.add_argument('--no-tiled', action='store_true', help='skip the extra tiled-layout measurement')
-    ap.add_argument('--lanes', type=int, default=int(os.environ.get('L3C_BENCH_LANES', 2)),
-                    help='decodes in flight in the pipelined mode (default 2)')
+    ap.add_argument('--lanes', type=int, default=int(os.environ.get('L3C_BENCH_LANES', 3)),
+                    help='decodes in flight in the pipelined mode (default 3)')
     ap.add_argument('--no-pipeline', dest='pipeline', action='store_false',
                     help='strictly sequential steps: encode(k), decode(k), encode(k+1), ...')
     args = ap.parse_args()

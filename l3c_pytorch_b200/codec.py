@@ -416,8 +416,8 @@ class BatchCodec(object):
         uses: `main` (decoder networks, CDF rows of the bottleneck scales), `bld[3]` (CDF-row builders of the
         R, G, B channels), `dec[3]` (the range decoders).  The `dec` streams of all lanes own a group of SMs
         (driver green contexts, l3c_partition_streams) sized for `L3C_DEC_WARPS_PER_SM` decoder-kernel warps
-        per SM (default 4 = one latency-bound warp per SM sub-partition; a decoder warp that shares its
-        scheduler with throughput-bound warps runs ~1.5x slower); everything else -- including the encode
+        per SM (default 4 for one lane = one latency-bound warp per SM sub-partition, 8 for several lanes; a
+        decoder warp that shares its scheduler with throughput-bound warps runs ~1.5x slower); everything else -- including the encode
         stream, which has the lowest priority -- runs on the remaining SMs.  Several lanes = several batches
         being decoded side by side: the decode of ONE batch is bound by the serial chain of its range coder
         and keeps only ~1/6 of the GPU busy.  L3C_SM_PARTITION=0, a driver without green contexts or an
@@ -436,7 +436,9 @@ class BatchCodec(object):
                 want_part = False
             if want_part:
                 n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-                wps = int(os.environ.get('L3C_DEC_WARPS_PER_SM', 4))
+                # one lane: 4 warps per SM (lowest latency); several lanes: 8 (measured at 16 x 512^2, 3 lanes: 36 SMs
+                # -> 81 Mpx/s, 72 SMs -> 63: what the decoders' group takes is lost to the throughput work)
+                wps = int(os.environ.get('L3C_DEC_WARPS_PER_SM', 4 if n_lanes == 1 else 8))
                 # every stream = decoder warp + helper warp (measured at 16 x 512^2, one lane, 4 warps per SM:
                 # 48 / 24 / 16 SMs -> decode 95 / 86 / 93 ms)
                 want = -(-(2 * n_decoders * n_lanes) // (8 * wps)) * 8
