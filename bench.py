@@ -571,7 +571,14 @@ def run_ours(args):
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    back, datas = run_e2e(args.steps)
+    if os.environ.get('L3C_BENCH_PROFILE'):           # where does the host thread spend an e2e step?
+        import cProfile
+        import pstats
+        prof = cProfile.Profile()
+        back, datas = prof.runcall(run_e2e, args.steps)
+        pstats.Stats(prof, stream=sys.stderr).sort_stats('cumulative').print_stats(35)
+    else:
+        back, datas = run_e2e(args.steps)
     e1.record()
     barrier()
     wall = time.perf_counter() - t0
