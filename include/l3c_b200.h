@@ -262,6 +262,17 @@ int l3c_symbols_to_values(const uint8_t *sym_dev, const float *values_dev, const
  * (dataloaders/images_loader.py:277-293 via PIL.Image.resize(BICUBIC); RGB baselines only). */
 int l3c_bicubic_half_u8(const uint8_t *in_dev, int N, int H, int W, uint8_t *out_dev, void *stream);
 
+/* RGB scale of a decode, channel-pipelined, as ONE host call (the runtime loop of codec.py moved into the
+ * library: ~400 launches and event operations per decode): chunk j of channel c-1 decoded -> rows of chunk j of
+ * channel c built on bld_streams[c] -> channel c's decoders resume on dec_streams[c] (state carried in the
+ * descriptors).  desc_dev_per_channel[c]: device array of N stream descriptors of channel c.  Ordered after
+ * `cur_stream`'s queue; `cur_stream` waits for all of it.  Reference: the strictly serial R -> G -> B loop of
+ * bitcoding.py:199-237. */
+int l3c_decode_rgb_pipelined(const float *l_dev, uint8_t *sym_dev, const float *targets_dev, int N, int HW, int K,
+                             int L, uint16_t *table_dev, int pitch,
+                             const l3c_dec_stream_t *const *desc_dev_per_channel, int chunk_px, void *cur_stream,
+                             void *const *bld_streams, void *const *dec_streams);
+
 /* ------------------------------------------------------------------------------------------
  * E. Execution resources
  * ---------------------------------------------------------------------------------------- */

@@ -367,44 +367,14 @@ class BatchCodec(object):
         N, HW = S.shape[0], S.shape[2] * S.shape[3]
         csz = max(2048, -(-HW // n_chunks))
         csz = -(-csz // 64) * 64
-        chunks = [(p0, min(csz, HW - p0)) for p0 in range(0, HW, csz)]
         state = torch.zeros(N * C * 4, dtype=torch.int32, device=dev)
         d['state'][:] = state.data_ptr() + 16 * (np.arange(N)[:, None] * C + np.arange(C)[None, :])
         descs = [E._desc_to_device(np.ascontiguousarray(d[:, c]), dev) for c in range(C)]
         cur = torch.cuda.current_stream()
         if lane is None:
             lane = self.lanes(dev, N * C, 1)[0][0]
-        s_bld, s_dec = lane.bld, lane.dec
-        start = torch.cuda.Event()
-        start.record(cur)
-        for st in s_bld[:C] + s_dec[:C]:
-            st.wait_event(start)
-        prev_dec = None
-        last = []
-        for (p0, npx) in chunks:
-            this_dec = []
-            for c in range(C):
-                with torch.cuda.stream(s_bld[c]):
-                    if c > 0:
-                        s_bld[c].wait_event(this_dec[c - 1])
-                    E.dmll_build_table(l, S, tg, C, K, L, True, c, table, pix0=p0, npix=npx)
-                    eb = torch.cuda.Event()
-                    eb.record(s_bld[c])
-                with torch.cuda.stream(s_dec[c]):
-                    s_dec[c].wait_event(eb)
-                    E.ac_decode_streams(None, dev, L, first=p0, count=npx, desc_dev=descs[c], n=N)
-                    ed = torch.cuda.Event()
-                    ed.record(s_dec[c])
-                this_dec.append(ed)
-            prev_dec = this_dec
-            last = this_dec
-        for ev in last:
-            cur.wait_event(ev)
-        for st in s_bld[:C]:
-            e = torch.cuda.Event()
-            e.record(st)
-            cur.wait_event(e)
-        del prev_dec
+        # the chunk loop itself (2 x 3 x n_chunks launches + as many event records / waits) runs inside the library
+        E.decode_rgb_pipelined(l, S, tg, K, L, table, descs, csz, cur, lane.bld, lane.dec)
 
     def encode_stream(self, dev, n_decoders, n_lanes=1):
         """A stream for encodes that run beside decodes (EncodeJob pipelining): confined to the SM group of

@@ -93,7 +93,7 @@ __device__ __forceinline__ uint32_t plane_cdf_u16(const float *__restrict__ mean
     for (int k = 0; k < K; ++k) {
         const float is = __fmul_rn(expf(-log_scales[k * N + n]), NEG_LOG2E);
         const float u = __fmul_rn(__fsub_rn(target, means[k * N + n]), is);
-        acc = __fmaf_rn(probs[k * N + n], sigmoid_from_log2(u), acc);
+        acc = mixture_term(acc, probs[k * N + n], u);
     }
     return (uint32_t)(__float2int_rn(__fmul_rn(acc, scale)) + l) & 0xFFFFu;
 }
@@ -328,4 +328,77 @@ extern "C" long long l3c_launch_log(char *buf, size_t cap, int reset) {
     }
     if (reset) g_log_n = 0;
     return total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// RGB scale of a decode, channel-pipelined (host-side runtime piece: one call instead of ~400 Python-level
+// launches / event operations per decode).  Channel c's means depend on the decoded channels < c of the same
+// pixel (logistic_mixture.py:262-272), so the reference codes R, G, B strictly one after the other; here the
+// three serial decoders run concurrently, staggered by one chunk of pixels: chunk j of channel c-1 decoded ->
+// rows of chunk j of channel c built (bld_streams[c]) -> channel c's warps resume from their saved state
+// (dec_streams[c]).  Everything is ordered after what `cur_stream` has queued, and `cur_stream` waits for it.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct EventRing {
+    std::vector<cudaEvent_t> ev;
+    size_t next = 0;
+    cudaEvent_t get() {
+        if (ev.size() < 64) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            ev.push_back(e);
+            return e;
+        }
+        return ev[next++ % ev.size()];      // a wait captures the record that precedes it in host order
+    }
+};
+}  // namespace
+
+extern "C" int l3c_decode_rgb_pipelined(const float *l_dev, uint8_t *sym_dev, const float *targets_dev, int N, int HW,
+                                        int K, int L, uint16_t *table_dev, int pitch,
+                                        const l3c_dec_stream_t *const *desc_dev_per_channel, int chunk_px,
+                                        void *cur_stream, void *const *bld_streams, void *const *dec_streams) {
+    L3C_REQUIRE(l_dev && sym_dev && targets_dev && table_dev && desc_dev_per_channel && bld_streams && dec_streams,
+                "l3c_decode_rgb_pipelined: null pointer");
+    L3C_REQUIRE(N >= 1 && HW >= 1 && chunk_px >= 1 && L == 256, "l3c_decode_rgb_pipelined: N=%d HW=%d chunk=%d L=%d", N, HW,
+                chunk_px, L);
+    thread_local EventRing rings[64];     // per host thread and device, for the lifetime of the process
+    int dev_id = 0;
+    L3C_CUDA(cudaGetDevice(&dev_id));
+    EventRing &ring = rings[dev_id & 63];
+    const int C = 3;
+    cudaStream_t cur = (cudaStream_t)cur_stream;
+    cudaEvent_t start = ring.get();
+    L3C_REQUIRE(start != nullptr, "l3c_decode_rgb_pipelined: cudaEventCreate failed");
+    L3C_CUDA(cudaEventRecord(start, cur));
+    for (int c = 0; c < C; ++c) {
+        L3C_CUDA(cudaStreamWaitEvent((cudaStream_t)bld_streams[c], start, 0));
+        L3C_CUDA(cudaStreamWaitEvent((cudaStream_t)dec_streams[c], start, 0));
+    }
+    cudaEvent_t dec_done[3] = {nullptr, nullptr, nullptr};
+    for (int p0 = 0; p0 < HW; p0 += chunk_px) {
+        const int npx = (HW - p0 < chunk_px) ? HW - p0 : chunk_px;
+        for (int c = 0; c < C; ++c) {
+            cudaStream_t sb = (cudaStream_t)bld_streams[c], sd = (cudaStream_t)dec_streams[c];
+            if (c > 0) L3C_CUDA(cudaStreamWaitEvent(sb, dec_done[c - 1], 0));      // this chunk of channel c-1 is decoded
+            if (int e = l3c_dmll_build_table(l_dev, sym_dev, targets_dev, N, HW, C, K, L, 1, c, p0, npx, table_dev, pitch, sb))
+                return e;
+            cudaEvent_t built = ring.get();
+            L3C_REQUIRE(built != nullptr, "l3c_decode_rgb_pipelined: cudaEventCreate failed");
+            L3C_CUDA(cudaEventRecord(built, sb));
+            L3C_CUDA(cudaStreamWaitEvent(sd, built, 0));
+            if (int e = l3c_ac_decode_streams(desc_dev_per_channel[c], N, L, (uint32_t)p0, (uint32_t)npx, sd)) return e;
+            dec_done[c] = ring.get();
+            L3C_REQUIRE(dec_done[c] != nullptr, "l3c_decode_rgb_pipelined: cudaEventCreate failed");
+            L3C_CUDA(cudaEventRecord(dec_done[c], sd));
+        }
+    }
+    for (int c = 0; c < C; ++c) {
+        L3C_CUDA(cudaStreamWaitEvent(cur, dec_done[c], 0));
+        cudaEvent_t e = ring.get();
+        L3C_REQUIRE(e != nullptr, "l3c_decode_rgb_pipelined: cudaEventCreate failed");
+        L3C_CUDA(cudaEventRecord(e, (cudaStream_t)bld_streams[c]));
+        L3C_CUDA(cudaStreamWaitEvent(cur, e, 0));
+    }
+    return L3C_OK;
 }
