@@ -541,7 +541,7 @@ conv1x1_f16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 // plain kernel, so both sides see identical integers).  Output: 4 B per coded sub-pixel.
 // Reference: criterion/logistic_mixture.py:248-275 + torchac_kernel.cu:26-76 after prob_clf.py:71-74.
 // ---------------------------------------------------------------------------------------------
-constexpr int LD_EPI_WARPS = 4;
+constexpr int LD_EPI_WARPS = 8;            // two groups of four (one warp per TMEM lane quarter), alternating tiles
 constexpr int LD_THREADS = 32 * (2 + LD_EPI_WARPS);
 
 struct ParamsLD {
@@ -599,7 +599,7 @@ lin_dmll_f16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull0 + 8u * a, 1);
-            mbar_init(tempty0 + 8u * a, LD_EPI_WARPS);
+            mbar_init(tempty0 + 8u * a, 4);               // drained by ONE group of four epilogue warps
         }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -661,10 +661,17 @@ lin_dmll_f16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
     } else {
         // ===================== epilogue: thread = pixel (TMEM lane 32*quarter + lane) =====================
+        // The per-pixel DMLL arithmetic is long dependent chains (exp, division, sigmoids): four warps cannot
+        // keep the SM's schedulers busy, so two groups of four take alternate tiles -- group g always drains
+        // accumulator g (the issuer alternates accumulators per tile).
         const int quarter = warp & 3;
+        const int grp = (warp - 2) >> 2;
         const float scale = (float)(65536 - p.L);            // 2^16 - (Lp - 1)
-        uint32_t acc = 0, acc_phase = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint32_t acc = (uint32_t)grp;
+        uint32_t acc_phase = 0;
+        int seq = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++seq) {
+            if ((seq & 1) != grp) continue;
             const long long pix = (long long)t * 128 + quarter * 32 + lane;
             const bool valid = pix < p.M;
             const int n = valid ? (int)(pix / p.HW) : 0;
@@ -724,8 +731,7 @@ lin_dmll_f16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
-            acc ^= 1u;
-            if (acc == 0) acc_phase ^= 1u;
+            acc_phase ^= 1u;
         }
     }
 
