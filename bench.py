@@ -454,9 +454,10 @@ def run_ours(args):
     for w in range(max(args.warmup, 1)):
         S, info = step_resident(dev_sets[w % n_sets])
     check_lossless(S, (max(args.warmup, 1) - 1) % n_sets, 'warm-up')
-    if args.pipeline:                      # the side stream has its own allocator pool: warm it up too
-        S, info = run_resident(max(args.warmup, 2))
-        check_lossless(S, (max(args.warmup, 2) - 1) % n_sets, 'pipelined warm-up')
+    if args.pipeline:                      # every lane / encode stream has its own allocator pool: warm them all up
+        n_warm = max(args.warmup, n_lanes + 1)     # (a first use inside the timed region costs a 300 ms cudaMalloc stall)
+        S, info = run_resident(n_warm)
+        check_lossless(S, (n_warm - 1) % n_sets, 'pipelined warm-up')
     sizes = info['sizes']
     counts = l3c_dist.gather_byte_counts(sizes, n_global * (n_units // n_img), rank, world)   # the one collective
     bpsp = l3c_dist.global_bpsp(counts, 3 * Hp * Wp)
@@ -543,7 +544,7 @@ def run_ours(args):
             t_seq, _ = timed_sequential(lambda i: step_resident(dev_sets[i]))
             t_pipe = None
             if args.pipeline:
-                run_resident(2)
+                run_resident(n_lanes + 1)
                 barrier()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
@@ -566,7 +567,7 @@ def run_ours(args):
     back, datas = step_e2e(0)
     assert torch.equal(back, raw_sets[0] if crops_mode else host_sets[0]), 'e2e round trip is not lossless'
     if args.pipeline:
-        run_e2e(2)
+        run_e2e(n_lanes + 1)
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -10,7 +10,8 @@ Layer types (the shapes an L3C round trip is made of):
   plain  3x3 64->64, fp32 output only
   tail   3x3 64->256 + PixelShuffle(2), 'act' (decoder features of scales 1, 2) / 'round' (scale 0)
   atr4   3x3 dilation 4 into a slice of the 192-channel concat buffer ('round')
-  lin    1x1 192->120 on the concat buffer (the DMLL parameters)
+  lin    1x1 192->120 on the concat buffer (the DMLL parameters); lin_fused: the same conv with the DMLL head in
+         its epilogue (coding intervals out, encode side; tf32: the two-step path for comparison)
   down   5x5 stride 2 (CUDA cores in every mode)
 Prints ms per launch, TFLOP/s, and algorithmic HBM bytes per launch / GB/s (what the layer must move, per
 DESIGN.md 4.1).
@@ -57,6 +58,8 @@ def main():
         cat = torch.randn(N, H, H, 192, device=dev).to(cat_dtype)
         cat_act = E.Act(None, cat) if mode == 'f16' else E.Act(cat, cat)
         mid = {}
+        sym = torch.randint(0, 256, (N, 3, H, H), dtype=torch.uint8, device=dev)
+        tgt = torch.linspace(-0.5, 255.5, 257, device=dev)
 
         def res1():
             mid['r'] = E.conv2d(c33, xa, relu=True, want='round')
@@ -79,6 +82,9 @@ def main():
                            64 * op_b + 256 * op_b),
             'atr4': (lambda: E.conv2d(catr, xa, out=cat, out_coff=64, want='round'), 2 * 9 * 64 * 64, 64 * op_b * 2),
             'lin': (lambda: E.conv2d(clin, cat_act), 2 * 192 * 120, 192 * op_b + 480),
+            'lin_fused': ((lambda: E.lin_dmll_intervals(clin, cat, sym, tgt, 3, 10, 256, True)) if mode == 'f16'
+                          else (lambda: E.dmll_intervals(E.conv2d(clin, cat_act), sym, tgt, 3, 10, 256, True)),
+                          2 * 192 * 120, 192 * op_b + 3 + 12),
             'down': (lambda: E.conv2d(cdown, x, want='act'), 2 * 25 * 64 * 64 / 4.0, 256 + (256 + 64 * op_b) / 4.0),
         }
         for name, (fn, flop_px, bytes_px) in cases.items():
