@@ -647,6 +647,8 @@ def run_ours(args):
     # a comparator, not part of the product path
     cudnn = {}
     try:
+        if args.no_comparators:
+            raise RuntimeError('skipped (--no-comparators)')
         xc = x.permute(0, 3, 1, 2)                    # NCHW view of the NHWC buffer = channels_last
         wc = conv1.weight.detach().contiguous(memory_format=torch.channels_last)
         for name, allow in (('tf32', True), ('fp32', False)):
@@ -784,7 +786,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='l3c', choices=sorted(WORKLOADS),
@@ -798,8 +800,10 @@ def main():
     ap.add_argument('--tile', type=int, nargs=2, default=None, metavar=('TH', 'TW'),
                     help='run the whole bench on TILED containers (throughput layout, not reference-compatible)')
     ap.add_argument('--no-tiled', action='store_true', help='skip the extra tiled-layout measurement')
-    ap.add_argument('--lanes', type=int, default=int(os.environ.get('L3C_BENCH_LANES', 3)),
-                    help='decodes in flight in the pipelined mode (default 3)')
+    ap.add_argument('--no-comparators', action='store_true',
+                    help='skip the cuDNN timings of the roofline shape (their autotuning floods a profiler capture)')
+    ap.add_argument('--lanes', type=int, default=int(os.environ.get('L3C_BENCH_LANES', 4)),
+                    help='decodes in flight in the pipelined mode (default 4)')
     ap.add_argument('--no-pipeline', dest='pipeline', action='store_false',
                     help='strictly sequential steps: encode(k), decode(k), encode(k+1), ...')
     args = ap.parse_args()

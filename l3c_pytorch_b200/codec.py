@@ -406,9 +406,10 @@ class BatchCodec(object):
                 want_part = False
             if want_part:
                 n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-                # one lane: 4 warps per SM (lowest latency); several lanes: 8 (measured at 16 x 512^2, 3 lanes: 36 SMs
-                # -> 81 Mpx/s, 72 SMs -> 63: what the decoders' group takes is lost to the throughput work)
-                wps = int(os.environ.get('L3C_DEC_WARPS_PER_SM', 4 if n_lanes == 1 else 8))
+                # one lane: 4 warps per SM (lowest latency); several lanes: 8, from four lanes on 12 (measured at
+                # 16 x 512^2: 3 lanes on 36 / 48 / 72 SMs -> 86 / 69 / 63 Mpx/s, 4 lanes on 32 / 48 SMs -> 89 / 80: what
+                # the decoders' group takes is lost to the throughput work)
+                wps = int(os.environ.get('L3C_DEC_WARPS_PER_SM', 4 if n_lanes == 1 else (8 if n_lanes <= 3 else 12)))
                 # every stream = decoder warp + helper warp (measured at 16 x 512^2, one lane, 4 warps per SM:
                 # 48 / 24 / 16 SMs -> decode 95 / 86 / 93 ms)
                 want = -(-(2 * n_decoders * n_lanes) // (8 * wps)) * 8
