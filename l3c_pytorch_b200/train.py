@@ -138,7 +138,7 @@ def training_loss(blueprint, x):
     conversion = np.log(2.) * num_subpixels
     costs_bpsp = [c / conversion for c in costs]
     final = int(np.prod(syms[-1].shape)) * np.log(net.config_ms.q.L) / conversion
-    return sum(costs_bpsp), [float(c) for c in costs_bpsp] + [float(final)]
+    return sum(costs_bpsp), [float(c.detach()) for c in costs_bpsp] + [float(final)]
 
 
 def make_optimizer(blueprint):
@@ -155,4 +155,4 @@ def train_step(blueprint, optimizer, img_batch):
     loss_pc, bpsps = training_loss(blueprint, img_batch)
     loss_pc.backward()
     optimizer.step()
-    return float(loss_pc), bpsps
+    return float(loss_pc.detach()), bpsps
