@@ -356,7 +356,7 @@ class BatchCodec(object):
             return S.cpu(), pads
         return S, pads
 
-    def _decode_rgb_pipelined(self, l, S, tg, C, K, L, table, d, dev, n_chunks=64, lane=None):
+    def _decode_rgb_pipelined(self, l, S, tg, C, K, L, table, d, dev, n_chunks=None, lane=None):
         """RGB scale: channel c's means depend on the decoded channels < c at the same pixel
         (logistic_mixture.py:262-272), so the reference codes R, G, B strictly one after the other.
         Here the three serial decoders run concurrently, staggered by one chunk of pixels: as soon as
@@ -365,6 +365,8 @@ class BatchCodec(object):
         carried across launches.  Serial depth drops from 3*HW to (1 + 2/n_chunks)*HW symbols (whole
         decode at 16x512^2 with 32 / 64 / 128 chunks: 120.5 / 118.7 / 117.7 ms when measured)."""
         N, HW = S.shape[0], S.shape[2] * S.shape[3]
+        if n_chunks is None:
+            n_chunks = int(os.environ.get('L3C_RGB_CHUNKS', 64))
         csz = max(2048, -(-HW // n_chunks))
         csz = -(-csz // 64) * 64
         state = torch.zeros(N * C * 4, dtype=torch.int32, device=dev)
