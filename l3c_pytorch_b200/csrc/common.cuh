@@ -44,6 +44,14 @@ void count_launch(const char *kernel_name);   // per-kernel launch counters (l3c
 int sm_count();                          // SMs of the current device
 int stream_sm_count(cudaStream_t st);    // SMs available to kernels launched into `st` (partition.cu)
 
+// cudaFuncSetAttribute is per DEVICE: "done once" flags must be kept per device, or a process that drives a second
+// GPU launches its kernels there without the opt-in for > 48 KB of dynamic shared memory
+static inline int current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev & 63;
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

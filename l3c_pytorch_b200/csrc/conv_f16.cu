@@ -762,7 +762,8 @@ int conv2d_f16(const l3c_conv_t &p, cudaStream_t st) {
     EncodeTiledFn encode = get_encode_fn();
     L3C_REQUIRE(encode != nullptr, "l3c_conv2d: cuTensorMapEncodeTiled is not available from the driver");
     const int n_sm = stream_sm_count(st);          // the stream may be confined to a group of SMs
-    static bool configured = false;
+    static bool configured_dev[64] = {};
+    bool &configured = configured_dev[current_device_slot()];
     if (!configured) {
         L3C_CUDA(cudaFuncSetAttribute(conv_f16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         L3C_CUDA(cudaFuncSetAttribute(conv_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -926,7 +927,8 @@ extern "C" int l3c_lin_dmll_intervals(const void *x_h, const void *w_h, const fl
     cudaStream_t st = (cudaStream_t)stream;
     EncodeTiledFn encode = get_encode_fn();
     L3C_REQUIRE(encode != nullptr, "l3c_lin_dmll_intervals: cuTensorMapEncodeTiled is not available from the driver");
-    static bool configured = false;
+    static bool configured_dev[64] = {};
+    bool &configured = configured_dev[current_device_slot()];
     if (!configured) {
         L3C_CUDA(cudaFuncSetAttribute(lin_dmll_f16_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         L3C_CUDA(cudaFuncSetAttribute(lin_dmll_f16_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -243,7 +243,8 @@ static int launch_conv(const l3c_conv_t &p, int Ho, int Wo, int pad, cudaStream_
     const size_t smem = ((size_t)HR * HC * CKP + 2 * CK * CO_TILE) * sizeof(float);
     L3C_REQUIRE(smem <= 227 * 1024, "l3c_conv2d: tile needs %zu B of shared memory", smem);
     auto kern = conv_ffma_kernel<KS, S>;
-    static size_t configured = 0;   // per (KS,S) instantiation
+    static size_t configured_dev[64] = {};   // per (KS,S) instantiation and device
+    size_t &configured = configured_dev[current_device_slot()];
     if (smem > configured) {
         L3C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;

@@ -623,7 +623,8 @@ int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st) {
     q.cout_rows = p.cout_pad;
     q.total_tiles = p.N * q.tiles_x * q.tiles_y * cout_tiles;
 
-    static bool configured = false;
+    static bool configured_dev[64] = {};
+    bool &configured = configured_dev[current_device_slot()];
     const int n_sm = stream_sm_count(st);          // the stream may be confined to a group of SMs
     if (!configured) {
         L3C_CUDA(cudaFuncSetAttribute(conv3x3_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

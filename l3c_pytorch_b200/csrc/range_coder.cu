@@ -1011,12 +1011,17 @@ extern "C" int l3c_ac_decode_streams(const l3c_dec_stream_t *streams_dev, int n_
         ac_decode32_kernel<<<grid, blk, 0, st>>>(streams_dev, n_streams, L, first, count);
     } else if (L == 256) {
         static int spc = 0;
+        static bool configured_dev[64] = {};
         if (spc == 0) {
             const char *e = getenv("L3C_DEC_SPC");
             spc = e ? atoi(e) : 1;
             if (spc != 1 && spc != 2 && spc != 4) spc = 1;
+        }
+        bool &configured = configured_dev[current_device_slot()];
+        if (!configured) {
             L3C_CUDA(cudaFuncSetAttribute(v3::ac_decode256_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           4 * v3::STREAM_SMEM));
+            configured = true;
         }
         if (spc == 4)
             v3::ac_decode256_kernel<4><<<ceil_div(n_streams, 4), 256, 4 * v3::STREAM_SMEM, st>>>(streams_dev, n_streams, first, count);
