@@ -7,7 +7,7 @@
 
 One "step" = one lossless round trip (encode -> decode) of one batch of synthetic images per GPU:
   l3c         16 x 3x512x512, L3C cr.cf                 (BASELINE configs[1] at N=1, configs[2] at N=8)
-  rgb_shared  32 x 3x256x256, cr_rgb_shared.cf, fp32    (configs[3])
+  rgb_shared  32 x 3x256x256, cr_rgb_shared.cf, f16x2   (configs[3])
   crops       1 x 3x3000x2000 per GPU -> 4 crops of 1500x1000 padded to 1504x1000 (configs[4], --gpus 4)
 Prints ONE JSON line (rank 0).  `value` = Mpixels/s with inputs resident in HBM; `e2e` = the same
 round trip through the public `Bitcoding` API from pinned host buffers (H2D of the images and the
@@ -41,7 +41,7 @@ WORKLOADS = {
                 flop_per_px=2.230e6,
                 name='L3C cr.cf (3 scales, seed-0 default init), %d x 3x512x512 uint8 noise images per GPU, '
                      'encode+decode round trip, byte-compatible .l3c containers'),
-    'rgb_shared': dict(cfg='cr_rgb_shared', n_img=32, H=256, W=256, precision='fp32', golden='rgbs_256x256',
+    'rgb_shared': dict(cfg='cr_rgb_shared', n_img=32, H=256, W=256, precision='f16x2', golden='rgbs_256x256',
                        flop_per_px=1.309e6,
                        name='RGB-shared baseline cr_rgb_shared.cf (bicubic thumbnail + 1 scale), %d x 3x256x256 '
                             'uint8 noise images per GPU, encode+decode round trip'),
@@ -612,7 +612,7 @@ def run_ours(args):
     # operand image.  With FP16 operands and layer-granular fp32 activations the layer is HBM-bound on a B200
     # (73.7 kFLOP per 256 / 768 algorithmic bytes per pixel vs a ridge of ~260 FLOP/B): the roofline is
     # algorithmic bytes / time against the measured copy bandwidth; the tensor-pipe view is reported beside it.
-    roof_prec = precision if precision != 'fp32' else 'f16'
+    roof_prec = precision if precision in ('f16', 'tf32') else 'f16'
     E.set_conv_precision(roof_prec)
     blk = bp.net.nets[0].dec.body[0].body
     conv1, conv2 = blk[0], blk[2]
@@ -745,13 +745,15 @@ def run_ours(args):
             'metric': METRIC, 'value': value, 'unit': 'Mpixels/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None,
-            'dtype': {'f16': 'f16', 'tf32': 'tf32', 'fp32': 'f32'}[precision], 'data': 'synthetic',
+            'dtype': {'f16': 'f16', 'tf32': 'tf32', 'fp32': 'f32', 'f16x2': 'f16x2'}[precision], 'data': 'synthetic',
             'config': {'workload': wl['name'] % n_img, 'bench_workload': args.workload,
                        'global_batch': n_global, 'parallelism': 'images sharded over %d GPU(s), no data-path '
                                                                 'collective' % world,
                        'conv_precision': precision + {'f16': ': FP16 operand images (RN), fp32 accumulation in TMEM, fp32 '
                                                              'residual stream and DMLL parameters; integer range coder',
                                                       'tf32': ': TF32-RN operands, fp32 accumulation',
+                                                      'f16x2': ': split-FP16 operands (hi + lo/2^11, 22 bits), three '
+                                                               'tcgen05.mma per K step, fp32 accumulation (strict mode)',
                                                       'fp32': ': CUDA-core fp32'}[precision],
                        'pipelining': ('%d decodes in flight (range decoders of all of them on one SM partition) beside '
                                       'the encodes of the next batches; all %d round trips, incl. the un-overlapped '
@@ -792,8 +794,8 @@ def main():
     ap.add_argument('--workload', default='l3c', choices=sorted(WORKLOADS),
                     help='l3c = BASELINE configs 2/3 (default), rgb_shared = config 4, crops = config 5')
     ap.add_argument('--precision', default=os.environ.get('L3C_CONV_PRECISION'),
-                    choices=['fp32', 'tf32', 'f16'],
-                    help='conv mode (default: f16 = FP16-operand tensor cores for l3c/crops, fp32 for rgb_shared)')
+                    choices=['fp32', 'tf32', 'f16', 'f16x2'],
+                    help='conv mode (default: f16 = FP16-operand tensor cores for l3c/crops, f16x2 = split-FP16 strict mode for rgb_shared)')
     ap.add_argument('--images-per-gpu', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--value-only', action='store_true', help='tuning: print the device-resident value and stop')

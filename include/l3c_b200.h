@@ -198,6 +198,12 @@ int l3c_dmll_sample(const float *l_dev, const float *u_sel_dev, const float *u_x
 #define L3C_PREC_TF32 1             /* tcgen05 kind::tf32 on operands pre-rounded to TF32 (RN), fp32 accumulate in TMEM */
 #define L3C_PREC_F16 2              /* tcgen05 kind::f16 on FP16 operand images (RN, saturating; the same 10 mantissa */
                                     /* bits as TF32-RN), fp32 accumulate in TMEM, fp32 residual stream               */
+#define L3C_PREC_F16X2 3            /* strict tensor-core mode: every operand is the sum of two FP16 numbers, hi = fp16(x) */
+                                    /* and lo = fp16((x - hi) * 2^11); a product is hi*hi + (hi*lo + lo*hi) / 2^11 = three   */
+                                    /* tcgen05.mma into two TMEM accumulators (the error-compensated split SURVEY section 7 */
+                                    /* asks for, with FP16 instead of TF32 pieces): ~2^-22 relative, i.e. fp32-class results  */
+                                    /* at several times the CUDA-core rate.  Operand images are [..][2*C] FP16: hi planes in  */
+                                    /* channels [0,C), lo planes in [C,2C); 3x3/s1/Cin=64 and 1x1 layers                      */
 
 typedef struct {
     const float *x;        /* dev NHWC [N][H][W][x_pitch] fp32, channels [0,Cin) read (FP32 / TF32 kernels)     */
@@ -218,6 +224,8 @@ typedef struct {
     int ksize, stride, dilation;   /* padding = ksize/2 if dilation==1 else dilation               */
     unsigned flags;
     int precision;
+    int yh_pitch;          /* element pitch of y_h when it differs from y_pitch (0 = same): split images are 2x as wide */
+    int yh_lo_off;         /* > 0: y_h is a SPLIT image (L3C_PREC_F16X2): lo plane yh_lo_off elements after the hi plane */
 } l3c_conv_t;
 
 int l3c_conv2d(const l3c_conv_t *p, void *stream);
@@ -244,6 +252,11 @@ int l3c_rgb_prep(const uint8_t *img_dev, const float *A1, const float *b1, const
  * (0 outside the image), elements 27..63 zero -- the 3 -> 64 conv then runs as a K = 64 GEMM on the tensor cores. */
 int l3c_rgb_im2col_f16(const uint8_t *img_dev, const float *A1, const float *b1, const float *A2, const float *b2,
                        int N, int H, int W, void *out_h_dev, void *stream);
+
+/* L3C_PREC_F16X2: fp32 [n_px][C] -> split operand image FP16 [n_px][2*C] (hi = fp16(x) in channels [0,C),
+ * lo = fp16((x - hi) * 2^11) in [C,2C)); C % 4 == 0.  For the outputs of the CUDA-core layers of that mode (no
+ * reference counterpart: the reference's convolutions are cuDNN fp32, pytorch_models/modules/edsr.py:33-38). */
+int l3c_split_f16x2(const float *x_dev, long long n_px, int C, void *out_h_dev, void *stream);
 
 /* to_q 1x1 conv + hard quantiser (net.py:116-148, quantizer.py:62-90):
  * sym = argmin_l (q - level_l)^2 (first minimum), bn_q = levels[sym].

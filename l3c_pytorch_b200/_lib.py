@@ -22,15 +22,15 @@ class ConvDesc(ctypes.Structure):
                 ('N', c_int), ('H', c_int), ('W', c_int), ('Cin', c_int), ('x_pitch', c_int),
                 ('Cout', c_int), ('cout_pad', c_int), ('y_pitch', c_int), ('y_coff', c_int),
                 ('ksize', c_int), ('stride', c_int), ('dilation', c_int),
-                ('flags', ctypes.c_uint), ('precision', c_int)]
+                ('flags', ctypes.c_uint), ('precision', c_int), ('yh_pitch', c_int), ('yh_lo_off', c_int)]
 
 
 CONV_RELU = 1
 CONV_PIXEL_SHUFFLE2 = 2
 CONV_ROUND_TF32 = 4
-PREC_FP32, PREC_TF32, PREC_F16 = 0, 1, 2
+PREC_FP32, PREC_TF32, PREC_F16, PREC_F16X2 = 0, 1, 2, 3
 E_UNSUPPORTED = -5          # L3C_EUNSUPPORTED
-PRECISIONS = {'fp32': PREC_FP32, 'tf32': PREC_TF32, 'f16': PREC_F16}
+PRECISIONS = {'fp32': PREC_FP32, 'tf32': PREC_TF32, 'f16': PREC_F16, 'f16x2': PREC_F16X2}
 
 # numpy dtypes of the stream descriptor structs (l3c_enc_stream_t / l3c_dec_stream_t)
 ENC_STREAM_DTYPE = [('intervals', '<u8'), ('out', '<u8'), ('n_sym', '<u4'), ('out_cap', '<u4')]
@@ -62,6 +62,7 @@ _SIGNATURES = {
     'l3c_conv2d': (c_int, [ctypes.POINTER(ConvDesc), c_void_p]),
     'l3c_lin_dmll_intervals': (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p, c_void_p]),
     'l3c_rgb_prep': (c_int, [c_void_p] * 5 + [c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'l3c_split_f16x2': (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p]),
     'l3c_rgb_im2col_f16': (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p, c_void_p]),
     'l3c_quantize_head': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p, c_void_p, c_void_p]),
     'l3c_symbols_to_values': (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_void_p]),

@@ -58,6 +58,7 @@ int sm_count() {
 int conv2d_ffma(const l3c_conv_t &p, cudaStream_t st);
 int conv2d_tcgen05(const l3c_conv_t &p, cudaStream_t st);
 int conv2d_f16(const l3c_conv_t &p, cudaStream_t st);
+int conv2d_f16x2(const l3c_conv_t &p, cudaStream_t st);
 
 // ---- helper kernels for the single-stream (reference-shaped) API -----------------------------
 
@@ -217,8 +218,9 @@ extern "C" int l3c_cuda_supported(void) {
 
 extern "C" int l3c_conv2d(const l3c_conv_t *p, void *stream) {
     L3C_REQUIRE(p && p->bias, "l3c_conv2d: null pointer");
-    if (p->precision == L3C_PREC_F16) {
-        L3C_REQUIRE(p->x_h && p->w_h && (p->y || p->y_h), "l3c_conv2d: F16 mode needs x_h, w_h and y or y_h");
+    L3C_REQUIRE(p->precision >= L3C_PREC_FP32 && p->precision <= L3C_PREC_F16X2, "l3c_conv2d: unknown precision %d", p->precision);
+    if (p->precision == L3C_PREC_F16 || p->precision == L3C_PREC_F16X2) {
+        L3C_REQUIRE(p->x_h && p->w_h && (p->y || p->y_h), "l3c_conv2d: F16 modes need x_h, w_h and y or y_h");
     } else {
         L3C_REQUIRE(p->x && p->w && p->y, "l3c_conv2d: null pointer");
     }
@@ -235,6 +237,7 @@ extern "C" int l3c_conv2d(const l3c_conv_t *p, void *stream) {
     }
     if (p->precision == L3C_PREC_FP32) return conv2d_ffma(*p, (cudaStream_t)stream);
     if (p->precision == L3C_PREC_F16) return conv2d_f16(*p, (cudaStream_t)stream);
+    if (p->precision == L3C_PREC_F16X2) return conv2d_f16x2(*p, (cudaStream_t)stream);
     return conv2d_tcgen05(*p, (cudaStream_t)stream);
 }
 

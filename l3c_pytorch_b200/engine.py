@@ -167,6 +167,43 @@ def _get_f16(self):
 PackedConv.get_f16 = _get_f16
 
 
+_LO_SCALE = 2048.0
+
+
+def _split_host(w):
+    """fp32 -> (hi, lo) FP16 pair with w ~= hi + lo / 2^11 (weight images; activations use l3c_split_f16x2)."""
+    hi = w.half()
+    lo = ((w - hi.float()) * _LO_SCALE).half()
+    return hi, lo
+
+
+def _get_f16x2(self):
+    """Split weight image of precision mode 'f16x2' (conv_f16x2.cu): 3x3 -> [9][cout_pad][128] (hi | lo per row),
+    1x1 -> [2 * Cin/64][cout_pad][64] (hi chunks, then lo chunks)."""
+    _, b = self.get()
+    if getattr(self, 'w_h2', None) is None or self._key_h2 != self._key:
+        w = self.conv.weight.detach().float().clamp(-65504.0, 65504.0)
+        cout, cin, kh, kw = w.shape
+        cout_pad = (cout + 63) // 64 * 64
+        assert cin % 64 == 0 and kh == kw and kh in (1, 3)
+        if kh == 3:
+            assert cin == 64
+            hi, lo = _split_host(w.permute(2, 3, 0, 1).reshape(9, cout, 64))
+            img = torch.zeros(9, cout_pad, 128, dtype=torch.float16, device=w.device)
+            img[:, :cout, :64] = hi
+            img[:, :cout, 64:] = lo
+        else:
+            hi, lo = _split_host(w.reshape(cout, cin // 64, 64).permute(1, 0, 2))
+            img = torch.zeros(2 * (cin // 64), cout_pad, 64, dtype=torch.float16, device=w.device)
+            img[:cin // 64, :cout] = hi
+            img[cin // 64:, :cout] = lo
+        self.w_h2, self._key_h2 = img.contiguous(), self._key
+    return self.w_h2, b
+
+
+PackedConv.get_f16x2 = _get_f16x2
+
+
 def round_to_tf32(t):
     """fp32 tensor -> nearest TF32-representable fp32 (10-bit mantissa, ties away from zero like
     `cvt.rna.tf32.f32`).  Host-side preparation of the tensor-core weight image."""
@@ -192,6 +229,8 @@ def as_operand(x):
         return Act(x)
     if f16_mode():
         return Act(x, x.clamp(-65504.0, 65504.0).half())
+    if f16x2_mode():
+        return Act(x, split_f16x2(x))
     return Act(x, round_to_tf32(x))
 
 
@@ -201,6 +240,21 @@ def tensor_core_mode():
 
 def f16_mode():
     return _PRECISION['mode'] == _lib.PREC_F16
+
+
+def f16x2_mode():
+    return _PRECISION['mode'] == _lib.PREC_F16X2
+
+
+def split_f16x2(x):
+    """fp32 NHWC [..., C] -> split operand image FP16 [..., 2C] (hi | lo) of precision mode 'f16x2'."""
+    require_cuda(x, 'x')
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    C = x.shape[-1]
+    out = torch.empty(x.shape[:-1] + (2 * C,), dtype=torch.float16, device=x.device)
+    check(lib.l3c_split_f16x2(_ptr(x), x.numel() // C, C, _ptr(out), _stream_ptr()))
+    LAUNCHES['n'] += 1
+    return out
 
 
 def _packed_obj(conv):
@@ -245,6 +299,8 @@ def conv2d(conv, x, cin=None, relu=False, residual=None, pixel_shuffle=False, ou
     mode = _PRECISION['mode'] if precision is None else precision
     if mode == _lib.PREC_F16:
         return _conv2d_f16(conv, xa, cin, relu, residual, pixel_shuffle, out, out_coff, want)
+    if mode == _lib.PREC_F16X2:
+        return _conv2d_f16x2(conv, xa, cin, relu, residual, pixel_shuffle, out, out_coff, want)
     x = xa.f
     require_cuda(x, 'x')
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
@@ -357,6 +413,94 @@ def _conv2d_f16(conv, xa, cin, relu, residual, pixel_shuffle, out, out_coff, wan
         assert y.shape == y_h.shape
     check(lib.l3c_conv2d(ctypes.byref(d), _stream_ptr()))
     LAUNCHES['n'] += 1
+    if want == 'plain':
+        return y
+    if want == 'round':
+        return Act(None, y_h)
+    return Act(y, y_h)
+
+
+def _conv2d_f16x2(conv, xa, cin, relu, residual, pixel_shuffle, out, out_coff, want):
+    """conv2d in precision mode 'f16x2' (strict tensor-core mode, conv_f16x2.cu): the 64-channel 3x3 layers and
+    the wide 1x1 layers read SPLIT operand images `xa.r` ([N,H,W,2*Cin] FP16, hi | lo) and accumulate hi*hi and
+    hi*lo + lo*hi separately; the other layers (5x5/s2, Cin = 3 or 5) run the fp32 FFMA kernel on `xa.f`, and
+    their output is split by l3c_split_f16x2 when a tensor-core layer follows ('act' / 'round')."""
+    src = xa.f if xa.f is not None else xa.r
+    require_cuda(src, 'x')
+    assert src.is_contiguous() and src.dim() == 4
+    N, H, W = src.shape[:3]
+    kh = conv.kernel_size[0]
+    stride, dil = conv.stride[0], conv.dilation[0]
+    cin_all = conv.in_channels
+    xp = src.shape[-1] if xa.f is not None else src.shape[-1] // 2
+    cin = cin_all if cin is None else cin
+    cout = conv.out_channels
+    pad = kh // 2 if dil == 1 else dil
+    Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    flags = (_lib.CONV_RELU if relu else 0) | (_lib.CONV_PIXEL_SHUFFLE2 if pixel_shuffle else 0)
+    co = cout // 4 if pixel_shuffle else cout
+    shape = (N, Ho * 2, Wo * 2, co) if pixel_shuffle else (N, Ho, Wo, co)
+    need_f, need_h = want in ('plain', 'act'), want in ('act', 'round')
+    y = y_h = None
+    if out is not None:
+        if want == 'round':
+            assert out.dtype == torch.float16      # split buffer [.., 2*Ctot]; this layer fills channels out_coff..
+            y_h = out
+        else:
+            assert out.dtype == torch.float32
+            y = out
+    tc = (xp == cin_all and cin == cin_all and stride == 1 and
+          ((kh == 3 and cin == 64 and cout % 64 == 0 and not (pixel_shuffle and residual is not None)) or
+           (kh == 1 and cin % 64 == 0 and not pixel_shuffle and cout % 2 == 0 and cout <= 256 and residual is None)))
+    k1 = tc and kh == 1
+    pc = _packed_obj(conv)
+    if need_f and y is None:
+        y = torch.empty(shape, dtype=torch.float32, device=src.device)
+    if tc and not k1:
+        if need_h and y_h is None:
+            y_h = torch.empty(shape[:3] + (2 * co,), dtype=torch.float16, device=src.device)
+        if xa.r is None or xa.r.dtype != torch.float16 or xa.r.shape[-1] != 2 * cin_all:
+            xa = Act(xa.f, split_f16x2(xa.f))
+        w_h, b = pc.get_f16x2()
+        yh_pitch = y_h.shape[-1] if y_h is not None else 0
+        d = ConvDesc(x_h=xa.r.data_ptr(), w_h=w_h.data_ptr(), bias=b.data_ptr(),
+                     residual=residual.data_ptr() if residual is not None else None,
+                     y=_dp(y), y_h=_dp(y_h), N=N, H=H, W=W, Cin=cin, x_pitch=2 * cin_all, Cout=cout,
+                     cout_pad=b.shape[0], y_pitch=y.shape[-1] if y is not None else yh_pitch // 2, y_coff=out_coff,
+                     ksize=kh, stride=stride, dilation=dil, flags=flags, precision=_lib.PREC_F16X2,
+                     yh_pitch=yh_pitch, yh_lo_off=yh_pitch // 2)
+        if residual is not None:
+            assert residual.dtype == torch.float32 and residual.is_contiguous() and out is None and \
+                tuple(residual.shape) == tuple(shape)
+        check(lib.l3c_conv2d(ctypes.byref(d), _stream_ptr()))
+        LAUNCHES['n'] += 1
+    else:
+        if y is None:
+            y = torch.empty(shape, dtype=torch.float32, device=src.device)
+        if k1:
+            if xa.r is None or xa.r.dtype != torch.float16 or xa.r.shape[-1] != 2 * cin_all:
+                xa = Act(xa.f, split_f16x2(xa.f))
+            w_h, b = pc.get_f16x2()
+            d = ConvDesc(x_h=xa.r.data_ptr(), w_h=w_h.data_ptr(), bias=b.data_ptr(), y=y.data_ptr(),
+                         N=N, H=H, W=W, Cin=cin, x_pitch=2 * cin_all, Cout=cout, cout_pad=b.shape[0],
+                         y_pitch=y.shape[-1], y_coff=out_coff, ksize=1, stride=1, dilation=1, flags=flags,
+                         precision=_lib.PREC_F16X2)
+        else:
+            assert xa.f is not None, 'an fp32 (CUDA-core) layer needs the fp32 activation'
+            w, b = pc.get()
+            d = ConvDesc(x=xa.f.data_ptr(), w=w.data_ptr(), bias=b.data_ptr(),
+                         residual=residual.data_ptr() if residual is not None else None, y=y.data_ptr(),
+                         N=N, H=H, W=W, Cin=cin, x_pitch=xa.f.shape[-1], Cout=cout, cout_pad=b.shape[0],
+                         y_pitch=y.shape[-1], y_coff=out_coff, ksize=kh, stride=stride, dilation=dil, flags=flags,
+                         precision=_lib.PREC_FP32)
+            if residual is not None:
+                assert residual.dtype == torch.float32 and residual.shape == y.shape and residual.is_contiguous()
+        check(lib.l3c_conv2d(ctypes.byref(d), _stream_ptr()))
+        LAUNCHES['n'] += 1
+        if need_h:
+            assert out is None or want != 'round', 'a CUDA-core layer cannot fill a slice of a split buffer'
+            y_h = split_f16x2(y)
     if want == 'plain':
         return y
     if want == 'round':

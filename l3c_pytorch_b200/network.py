@@ -242,10 +242,12 @@ class StackedAtrousConvs(nn.Module):
         """x: engine.Act -> NHWC parameter tensor; or, with fused = (sym uint8 planes, dmll) in f16 mode, the
         coding intervals of `sym` (the DMLL head runs in the 1x1 conv's epilogue: engine.lin_dmll_intervals)."""
         src = x.f if x.f is not None else x.r
-        N, H, W, Cin = src.shape
-        # f16 mode: the concat buffer IS the FP16 operand image of the 1x1 conv
-        cat = torch.empty(N, H, W, Cin * len(self.atrous), device=src.device,
-                          dtype=torch.float16 if E.f16_mode() else torch.float32)
+        N, H, W = src.shape[:3]
+        Cin = self.atrous[0].in_channels
+        # f16 modes: the concat buffer IS the FP16 operand image of the 1x1 conv (f16x2: the split image, hi | lo)
+        f16 = E.f16_mode() or E.f16x2_mode()
+        cat = torch.empty(N, H, W, Cin * len(self.atrous) * (2 if E.f16x2_mode() else 1), device=src.device,
+                          dtype=torch.float16 if f16 else torch.float32)
         for i, a in enumerate(self.atrous):
             # concat by channel slice; `cat` only feeds the 1x1 conv -> TF32-rounded in place when the
             # tensor cores are on
@@ -255,7 +257,7 @@ class StackedAtrousConvs(nn.Module):
             C = sym.shape[1]
             return E.lin_dmll_intervals(self.lin, cat, sym, dm.targets(cat.device), C,
                                         self.lin.out_channels // ((4 if dm.rgb_scale else 3) * C), dm.L, dm.rgb_scale)
-        return E.conv2d(self.lin, E.Act(None, cat) if E.f16_mode() else cat)
+        return E.conv2d(self.lin, E.Act(None, cat) if f16 else cat)
 
 
 class AtrousProbabilityClassifier(nn.Module):

@@ -347,3 +347,106 @@ def test_rgb_head_im2col_gemm(H, W):
     finally:
         net.cuda()
     np.testing.assert_allclose(got.r.float().cpu().permute(0, 3, 1, 2).numpy(), want.numpy(), rtol=2e-3, atol=2e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# precision mode 'f16x2': split-FP16 operands (hi + lo / 2^11), three MMAs per K step, two TMEM accumulators
+# ---------------------------------------------------------------------------------------------
+def _unsplit(img):
+    """split image [..., 2C] -> the fp32 value it stands for"""
+    C = img.shape[-1] // 2
+    return img[..., :C].float() + img[..., C:].float() / 2048.0
+
+
+@pytest.mark.parametrize('cout,rate,H,W,kw', [(64, 1, 16, 16, {}), (64, 2, 24, 40, {}), (64, 4, 19, 37, {}),
+                                              (256, 1, 12, 20, dict(pixel_shuffle=True)), (64, 1, 8, 16, dict(relu=True)),
+                                              (64, 1, 3, 5, {}), (64, 1, 40, 72, dict(residual=True)),
+                                              (128, 1, 17, 33, dict(relu=True)), (64, 4, 64, 48, dict(residual=True))])
+def test_f16x2_conv_vs_torch_fp32(cout, rate, H, W, kw):
+    """conv_f16x2.cu against a PyTorch conv in float64 on the UNROUNDED fp32 operands, at the tolerance of the
+    CUDA-core fp32 kernel (RTOL / ATOL of test_conv_vs_torch): the split carries 22 significant bits per operand.
+    The output modes agree bit for bit, the split image of the output reproduces it to 2^-21, and a channel-slice
+    write leaves the neighbours alone."""
+    from l3c_pytorch_b200 import engine as E, _lib
+    P = _lib.PREC_F16X2
+    kw = dict(kw)
+    conv = _conv_module(64, cout, 3, 1, rate)
+    x = torch.randn(3, 64, H, W)
+    x[0, :, 0, 0] = 1e-6
+    want = F.conv2d(x.double(), conv.weight.detach().double(), conv.bias.detach().double(), padding=rate, dilation=rate)
+    res = None
+    if kw.pop('residual', False):
+        r = torch.randn(3, cout, H, W)
+        want = want + r.double()
+        res = _nhwc(r)
+    if kw.get('relu'):
+        want = F.relu(want)
+    if kw.get('pixel_shuffle'):
+        want = F.pixel_shuffle(want, 2)
+    xf = _nhwc(x)
+    xa = E.Act(xf, E.split_f16x2(xf))
+    np.testing.assert_allclose(_unsplit(xa.r).cpu().numpy(), xf.cpu().numpy(), rtol=2.0 ** -20, atol=1e-9)
+    cc = conv.cuda()
+    got = E.conv2d(cc, xa, precision=P, want='act', residual=res, **kw)
+    np.testing.assert_allclose(got.f.cpu().permute(0, 3, 1, 2).numpy(), want.float().numpy(), rtol=RTOL, atol=ATOL)
+    co = got.f.shape[-1]
+    assert got.r.dtype == torch.float16 and got.r.shape[-1] == 2 * co
+    np.testing.assert_allclose(_unsplit(got.r).cpu().numpy(), got.f.cpu().numpy(), rtol=2.0 ** -20, atol=1e-9)
+    plain = E.conv2d(cc, xa, precision=P, want='plain', residual=res, **kw)
+    assert torch.equal(plain, got.f)
+    r_only = E.conv2d(cc, xa, precision=P, want='round', residual=res, **kw)
+    assert r_only.f is None and torch.equal(r_only.r, got.r)
+    if not kw.get('pixel_shuffle') and res is None:
+        buf = torch.full((3, H, W, 2 * 3 * cout), 7.0, dtype=torch.float16, device='cuda')
+        E.conv2d(cc, xa, precision=P, want='round', out=buf, out_coff=cout, **kw)
+        assert torch.equal(buf[..., cout:2 * cout], got.r[..., :cout])
+        assert torch.equal(buf[..., 4 * cout:5 * cout], got.r[..., cout:])
+        for lo, hi in ((0, cout), (2 * cout, 4 * cout), (5 * cout, 6 * cout)):
+            assert bool((buf[..., lo:hi] == 7).all())
+
+
+@pytest.mark.parametrize('cin,cout,H,W', [(192, 120, 9, 31), (192, 150, 16, 16), (64, 64, 8, 16), (192, 120, 64, 64),
+                                          (128, 256, 5, 7)])
+def test_f16x2_1x1_conv(cin, cout, H, W):
+    from l3c_pytorch_b200 import engine as E, _lib
+    conv = _conv_module(cin, cout, 1)
+    x = torch.randn(2, cin, H, W)
+    want = F.conv2d(x.double(), conv.weight.detach().double(), conv.bias.detach().double()).float()
+    xa = E.Act(None, E.split_f16x2(_nhwc(x)))
+    got = E.conv2d(conv.cuda(), xa, precision=_lib.PREC_F16X2)
+    assert got.shape == (2, H, W, cout) and got.dtype == torch.float32
+    np.testing.assert_allclose(got.cpu().permute(0, 3, 1, 2).numpy(), want.numpy(), rtol=RTOL, atol=ATOL)
+    got = E.conv2d(conv.cuda(), xa, precision=_lib.PREC_F16X2, relu=True)
+    np.testing.assert_allclose(got.cpu().permute(0, 3, 1, 2).numpy(), F.relu(want).numpy(), rtol=RTOL, atol=ATOL)
+
+
+def test_f16x2_is_much_closer_to_fp32_than_the_fast_modes():
+    """what the strict mode is for: error against float64 ~1000x below the f16 / tf32 modes' (same layer, same
+    input), within a small factor of the CUDA-core fp32 kernel's"""
+    from l3c_pytorch_b200 import engine as E, _lib
+    conv = _conv_module(64, 64, 3)
+    x = torch.randn(2, 64, 48, 64)
+    want = F.conv2d(x.double(), conv.weight.detach().double(), conv.bias.detach().double(), padding=1)
+    cc = conv.cuda()
+    err = {}
+    xf = _nhwc(x)
+    for name, p in (('fp32', _lib.PREC_FP32), ('f16', _lib.PREC_F16), ('f16x2', _lib.PREC_F16X2)):
+        got = E.conv2d(cc, E.Act(xf, xf.half()) if name == 'f16' else xf, precision=p).cpu().permute(0, 3, 1, 2).double()
+        err[name] = float((got - want).abs().max())
+    assert err['f16x2'] < err['f16'] / 200, err
+    assert err['f16x2'] < 8 * err['fp32'] + 1e-6, err
+
+
+def test_f16x2_conv_independent_of_batch_and_position():
+    from l3c_pytorch_b200 import engine as E, _lib
+    P = _lib.PREC_F16X2
+    conv = _conv_module(64, 64, 3).cuda()
+    x = torch.randn(5, 64, 40, 56)
+    r = E.split_f16x2(_nhwc(x))
+    full = E.conv2d(conv, E.Act(None, r), precision=P)
+    one = E.conv2d(conv, E.Act(None, r[3:4].contiguous()), precision=P)
+    assert torch.equal(full[3:4], one)
+    big = torch.zeros(1, 80, 112, 128, dtype=torch.float16, device='cuda')
+    big[0, 24:64, 40:96] = r[3]
+    moved = E.conv2d(conv, E.Act(None, big), precision=P)
+    assert torch.equal(moved[0, 25:63, 41:95], full[3, 1:39, 1:55])

@@ -54,9 +54,9 @@ def main():
         x = torch.randn(N, H, H, 64, device=dev)
         xa = E.as_operand(x)
         res = torch.randn(N, H, H, 64, device=dev)
-        cat_dtype = torch.float16 if mode == 'f16' else torch.float32
-        cat = torch.randn(N, H, H, 192, device=dev).to(cat_dtype)
-        cat_act = E.Act(None, cat) if mode == 'f16' else E.Act(cat, cat)
+        cat_dtype = torch.float16 if mode in ('f16', 'f16x2') else torch.float32
+        cat = torch.randn(N, H, H, 384 if mode == 'f16x2' else 192, device=dev).to(cat_dtype)
+        cat_act = E.Act(None, cat) if mode in ('f16', 'f16x2') else E.Act(cat, cat)
         mid = {}
         sym = torch.randint(0, 256, (N, 3, H, H), dtype=torch.uint8, device=dev)
         tgt = torch.linspace(-0.5, 255.5, 257, device=dev)
