@@ -327,7 +327,7 @@ def run_ours(args):
     n_lanes = max(1, args.lanes)
     lanes, side_stream = codec.lanes(dev, 3 * n_units, n_lanes)[:2] if args.pipeline else (None, None)
     enc_streams = codec.encode_streams(dev, 3 * n_units, n_lanes) if args.pipeline else None
-    ENC_DEPTH = int(os.environ.get('L3C_BENCH_ENC_DEPTH', 2))
+    ENC_DEPTH = int(os.environ.get('L3C_BENCH_ENC_DEPTH', len(enc_streams) if enc_streams else 2))
 
     def run_resident(steps, first_set=0):
         if not args.pipeline:
@@ -358,14 +358,26 @@ def run_ours(args):
                         tl.append(('enc', i, a, tick(es)))
 
         t_origin = tick(cur) if dbg else None
-        for i in range(ENC_DEPTH):
-            begin(i)
+        only = os.environ.get('L3C_BENCH_ONLY')       # diagnosis: 'enc' / 'dec' = only that half of every step
+        if only == 'dec':
+            begin(0)
+            blob0, info0 = jobs.pop(0).finish(to_host=False)
+        else:
+            for i in range(ENC_DEPTH):
+                begin(i)
         for s in range(steps):
             t0 = time.perf_counter()
-            blob, info = jobs.pop(s).finish(to_host=False)
+            if only == 'dec':
+                blob, info = blob0, info0
+            else:
+                blob, info = jobs.pop(s).finish(to_host=False)
             t1 = time.perf_counter()
-            begin(s + ENC_DEPTH)
+            if only != 'dec':
+                begin(s + ENC_DEPTH)
             t2 = time.perf_counter()
+            if only == 'enc':
+                S = None
+                continue
             ln = lanes[s % n_lanes]
             with torch.cuda.stream(ln.main):
                 ln.main.wait_event(info['ready'])
@@ -443,6 +455,8 @@ def run_ours(args):
         return back, datas
 
     def check_lossless(S, k, what):
+        if os.environ.get('L3C_BENCH_ONLY'):      # diagnosis runs time half a step: nothing to compare
+            return
         assert torch.equal(S, dev_sets[k]), what + ': round trip is not lossless'
         if crops_mode:       # undo the padding, stitch the crops back (auto_crop.py:109-136): the user's image
             per = n_units // n_img

@@ -398,6 +398,9 @@ class BatchCodec(object):
         cache = self.__dict__.setdefault('_lane_cache', {})
         if key not in cache:
             part = None
+            # encode streams: an encode is a throughput phase (the networks) followed by a latency-bound one (the
+            # range encoders, ~19 ms on one warp per stream); encodes on the same stream run one after the other
+            n_enc = max(1, int(os.environ.get('L3C_ENC_STREAMS', 2)))
             want_part = os.environ.get('L3C_SM_PARTITION', '1') != '0'
             if want_part and _under_injection_tool() and 'L3C_SM_PARTITION' not in os.environ:
                 # Nsight Compute cannot profile kernels launched into green-context streams (it lost the
@@ -417,7 +420,7 @@ class BatchCodec(object):
                 want = -(-(2 * n_decoders * n_lanes) // (8 * wps)) * 8
                 want = min(max(8, want), (n_sm // 16) * 8)
                 want = int(os.environ.get('L3C_DEC_SMS', want))           # bring-up knob
-                part = E.partition_streams2(dev, want, 3 * n_lanes, 4 * n_lanes, 2)
+                part = E.partition_streams2(dev, want, 3 * n_lanes, 4 * n_lanes, n_enc)
             lanes = []
             for i in range(n_lanes):
                 ln = DecodeLane()
@@ -435,7 +438,7 @@ class BatchCodec(object):
                 lanes.append(ln)
             # two encode streams (default priority): the range-encoder launch of one batch is latency-bound (one
             # warp per stream, ~16 ms) and overlaps the convs of the next batch when they alternate
-            encs = part[2] if part is not None else [torch.cuda.Stream(device=dev) for _ in range(2)]
+            encs = part[2] if part is not None else [torch.cuda.Stream(device=dev) for _ in range(n_enc)]
             cache[key] = (lanes, encs[0], encs)
         return cache[key]
 

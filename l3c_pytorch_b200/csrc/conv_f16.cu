@@ -33,6 +33,7 @@
 // Accumulation order per output element: (dx, dy, k-step) -- fixed, independent of batch / image size /
 // tile position / pipe: encoder-side and decoder-side evaluations are bit-identical.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -745,6 +746,21 @@ lin_dmll_f16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
 }  // namespace f16
 
+// dynamic shared memory a conv CTA may take (bytes).  Default: everything an SM has (227 KB).  L3C_CONV_SMEM_KB
+// lowers it so that small latency-bound CTAs (the range decoders: 16 KB per stream) can be resident BESIDE a
+// conv CTA when no SM partition separates them (codec.lanes, L3C_SM_PARTITION=0).
+static int conv_smem_cap() {
+    static int cap = 0;
+    if (cap == 0) {
+        const char *e = getenv("L3C_CONV_SMEM_KB");
+        int kb = e ? atoi(e) : 227;
+        if (kb < 112) kb = 112;
+        if (kb > 227) kb = 227;
+        cap = kb * 1024;
+    }
+    return cap;
+}
+
 // operand image x_h: fp16 NHWC [N][H][W][x_pitch]; weight image w_h (engine.PackedConv.get_f16):
 //   3x3: [tap 9][cout_pad][64] fp16      1x1: [Cin/64][cout_pad][64] fp16     (rows of 128 B)
 int conv2d_f16(const l3c_conv_t &p, cudaStream_t st) {
@@ -781,8 +797,9 @@ int conv2d_f16(const l3c_conv_t &p, cudaStream_t st) {
         const int a_rows = TH + 2 * d;
         L3C_REQUIRE(a_rows <= 256, "l3c_conv2d[f16]: dilation %d too large", d);
         const int a_bytes = a_rows * TW * 128;
-        int n_stages = (227 * 1024 - 1024 - 512 - W_RES_BYTES) / (PIPES * a_bytes);      // per pipe
+        int n_stages = (conv_smem_cap() - 1024 - 512 - W_RES_BYTES) / (PIPES * a_bytes);      // per pipe
         if (n_stages > 3) n_stages = 3;
+        if (n_stages < 1 && PIPES * a_bytes <= 227 * 1024 - 1024 - 512 - W_RES_BYTES) n_stages = 1;   // above the cap
         L3C_REQUIRE(n_stages >= 1, "l3c_conv2d[f16]: halo of dilation %d does not fit in shared memory", d);
         {
             cuuint64_t dims[4] = {64, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
@@ -860,7 +877,7 @@ int conv2d_f16(const l3c_conv_t &p, cudaStream_t st) {
         int per_ct = n_sm / cout_tiles;
         if (per_ct < 1) per_ct = 1;
         if (per_ct > ptiles) per_ct = ptiles;
-        const int n_stages = 2;
+        const int n_stages = (conv_smem_cap() - 1024 - 512) / (PIPES * K5_STAGE_BYTES) >= 2 ? 2 : 1;
         const int smem_bytes = PIPES * n_stages * K5_STAGE_BYTES + 1024 + 512;
         conv_f16_kernel<1><<<dim3(per_ct, cout_tiles), THREADS, smem_bytes, st>>>(map_x, map_w, q, n_stages, K5_STAGE_BYTES, ptiles);
         L3C_LAUNCH_CHECK("conv5x5s2_f16_kernel");
@@ -873,7 +890,8 @@ int conv2d_f16(const l3c_conv_t &p, cudaStream_t st) {
     const int kchunks = p.Cin / 64;
     const long long M = (long long)p.N * p.H * p.W;
     const int w_bytes = kchunks * p.cout_pad * 128;
-    int n_stages = (227 * 1024 - 1024 - 512 - w_bytes) / K1_A_BYTES;
+    int n_stages = (conv_smem_cap() - 1024 - 512 - w_bytes) / K1_A_BYTES;
+    if (n_stages < 1 && w_bytes + K1_A_BYTES <= 227 * 1024 - 1024 - 512) n_stages = 1;
     if (n_stages > K1_MAX_STAGES) n_stages = K1_MAX_STAGES;
     L3C_REQUIRE(n_stages >= 2, "l3c_conv2d[f16]: weights of a %d -> %d 1x1 layer do not fit in shared memory", p.Cin, p.Cout);
     {
@@ -937,7 +955,8 @@ extern "C" int l3c_lin_dmll_intervals(const void *x_h, const void *w_h, const fl
     const int kchunks = Cin / 64;
     const long long M = (long long)N * HW;
     const int w_bytes = kchunks * npad * 128;
-    int n_stages = (227 * 1024 - 1024 - 512 - w_bytes) / K1_A_BYTES;
+    int n_stages = (conv_smem_cap() - 1024 - 512 - w_bytes) / K1_A_BYTES;
+    if (n_stages < 1 && w_bytes + K1_A_BYTES <= 227 * 1024 - 1024 - 512) n_stages = 1;
     if (n_stages > K1_MAX_STAGES) n_stages = K1_MAX_STAGES;
     L3C_REQUIRE(n_stages >= 2, "l3c_lin_dmll_intervals: weights do not fit in shared memory (Cin=%d)", Cin);
     alignas(64) CUtensorMap map_x, map_w;
