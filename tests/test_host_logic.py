@@ -310,3 +310,43 @@ def test_tiled_container_layout_and_parser_round_trip():
         assert [o for (o, _) in flat] == list(offs) and [n for (_, n) in flat] == [int(x) for x in lens]
         if tile is None:
             assert data[8] == 5 and struct.unpack_from('<HH', data, 9) == (8, 12)      # reference layout untouched
+
+
+def test_f16x2_split_weight_images():
+    """host side of precision mode 'f16x2' (engine.PackedConv.get_f16x2 uses engine._split_host): hi + lo / 2^11
+    reproduces an fp32 weight to 2^-21 relative, the images have the layout conv_f16x2.cu's TMA maps read
+    (3x3: [9][cout_pad][hi 64 | lo 64], 1x1: [hi chunks..., lo chunks...][cout_pad][64]), padding rows are zero."""
+    import numpy as np
+    import torch
+    from l3c_pytorch_b200 import engine as E
+    torch.manual_seed(3)
+    w = torch.randn(1000) * torch.logspace(-6, 3, 1000)
+    hi, lo = E._split_host(w)
+    assert hi.dtype == torch.float16 and lo.dtype == torch.float16
+    back = hi.double() + lo.double() / 2048.0
+    big = w.abs() > 1e-3                     # above the FP16 subnormal range the split carries 22 bits
+    assert float(((back - w.double()).abs() / w.double().abs())[big].max()) < 2.0 ** -21
+    assert float((back - w.double()).abs()[~big].max()) < 1e-9
+
+    class FakePacked(E.PackedConv):
+        def get(self):                       # no device repack on a CPU box: only the split image is under test
+            self._key = 'k'
+            cout = self.conv.weight.shape[0]
+            return None, torch.zeros((cout + 63) // 64 * 64)
+
+    for k, cin, cout in ((3, 64, 64), (3, 64, 256), (1, 192, 120), (1, 64, 10)):
+        conv = torch.nn.Conv2d(cin, cout, k)
+        img, b = FakePacked(conv).get_f16x2()
+        cp = b.shape[0]
+        wd = conv.weight.detach()
+        if k == 3:
+            assert tuple(img.shape) == (9, cp, 128)
+            val = img[:, :, :64].double() + img[:, :, 64:].double() / 2048.0          # [tap][cout][cin]
+            want = wd.permute(2, 3, 0, 1).reshape(9, cout, 64).double()
+        else:
+            nch = cin // 64
+            assert tuple(img.shape) == (2 * nch, cp, 64)
+            val = img[:nch].double() + img[nch:].double() / 2048.0                    # [chunk][cout][64]
+            want = wd.reshape(cout, nch, 64).permute(1, 0, 2).double()
+        np.testing.assert_allclose(val[:, :cout].numpy(), want.numpy(), rtol=2.0 ** -20, atol=1e-9)
+        assert bool((img[:, cout:] == 0).all())
