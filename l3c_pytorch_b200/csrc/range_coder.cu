@@ -746,6 +746,39 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 constexpr int RING_BYTES = R * 2 * 32 * 16;           // 16 KB of proposals per stream
 constexpr int STREAM_SMEM = RING_BYTES + 128;         // + tops[R] (64 B) + 4 mbarriers (32 B), 16-byte aligned
 
+// one speculative group of G symbols (decoder warp).  FULL2: the group starts with a span of exactly 2^32.
+template <bool FULL2>
+__device__ __forceinline__ bool spec_group(CoderState &cs, BitSource &src, const uint4 *slot, uint32_t *tops, int lane) {
+    bool bad = false;
+    uint4 a = slot[0], b = slot[32];
+#pragma unroll 1
+    for (int d = 0; d < G; ++d) {
+        const uint4 *nslot = slot + ((d + 1) & (G - 1)) * 64;         // next symbol's proposals
+        const uint4 na = nslot[0], nb = nslot[32];
+        const uint32_t r = cs.r, dv = cs.dv;
+        const uint32_t span = r + 1u;                                 // 2^32 wraps to 0
+        bad |= (dv > r) || ((span == 0u) != FULL2);
+        // cdf[m] <= count  <=>  cdf[m] * span < (dv + 1) << 16  <=>  mulhi(cdf[m] << 16, span) <= dv
+        const uint32_t pk[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        bool f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            f[j] = (FULL2 ? (pk[j] & 0xFFFF0000u) : __umulhi(pk[j] & 0xFFFF0000u, span)) <= dv;
+        f[0] = f[0] || (lane == 0);                                   // symbol 0 is the floor
+        // rows are sorted: the last passing proposal is the numerically largest
+        const uint32_t m01 = f[1] ? pk[1] : (f[0] ? pk[0] : 0u);
+        const uint32_t m23 = f[3] ? pk[3] : (f[2] ? pk[2] : 0u);
+        const uint32_t m45 = f[5] ? pk[5] : (f[4] ? pk[4] : 0u);
+        const uint32_t m67 = f[7] ? pk[7] : (f[6] ? pk[6] : 0u);
+        const uint32_t top = __reduce_max_sync(FULL, max(max(m01, m23), max(m45, m67)));
+        if (lane == 0) tops[d] = top;
+        bad |= cs.update_flat(top >> 16, (top & 0xFFFFu) + 1u, src);
+        a = na;
+        b = nb;
+    }
+    return bad;
+}
+
 template <int SPC>
 __global__ void __launch_bounds__(64 * SPC)
 ac_decode256_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams, uint32_t first, uint32_t count) {
@@ -881,33 +914,14 @@ ac_decode256_kernel(const l3c_dec_stream_t *__restrict__ streams, int n_streams,
             // renormalisation shifts -- only set a sticky flag; the group is then replayed exactly.
             const CoderState cs0 = cs;
             const BitSource src0 = src;
-            bool bad = false;
             const uint4 *slot = &ring[g * G][0][lane];
-            uint4 a = slot[0], b = slot[32];
-#pragma unroll 1
-            for (int d = 0; d < G; ++d) {
-                const uint4 *nslot = slot + ((d + 1) & (G - 1)) * 64;         // next symbol's proposals
-                const uint4 na = nslot[0], nb = nslot[32];
-                const uint32_t r = cs.r, dv = cs.dv;
-                const uint32_t span = r + 1u;                                 // 2^32 wraps to 0: replay (stream start)
-                bad |= (dv > r) || (span == 0u);
-                // cdf[m] <= count  <=>  cdf[m] * span < (dv + 1) << 16  <=>  mulhi(cdf[m] << 16, span) <= dv
-                const uint32_t pk[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                bool f[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __umulhi(pk[j] & 0xFFFF0000u, span) <= dv;
-                f[0] = f[0] || (lane == 0);                                   // symbol 0 is the floor
-                // rows are sorted: the last passing proposal is the numerically largest
-                const uint32_t m01 = f[1] ? pk[1] : (f[0] ? pk[0] : 0u);
-                const uint32_t m23 = f[3] ? pk[3] : (f[2] ? pk[2] : 0u);
-                const uint32_t m45 = f[5] ? pk[5] : (f[4] ? pk[4] : 0u);
-                const uint32_t m67 = f[7] ? pk[7] : (f[6] ? pk[6] : 0u);
-                const uint32_t top = __reduce_max_sync(FULL, max(max(m01, m23), max(m45, m67)));
-                if (lane == 0) tops[g * G + d] = top;
-                bad |= cs.update_flat(top >> 16, (top & 0xFFFFu) + 1u, src);
-                a = na;
-                b = nb;
-            }
+            // A span of exactly 2^32 (r + 1 wraps to 0) is the state of a stream's first symbol -- and of EVERY
+            // symbol when all probabilities are the same power of two (the uniform prior with L = 256: each
+            // symbol narrows the interval to 2^24 and renormalises by exactly 8 bits; such streams used to replay
+            // every group: 495 ns per symbol).  mulhi(x, 2^32) = x: those groups run a second copy of the loop
+            // without the multiply; a group that mixes the two kinds of state sets `bad` and is replayed.
+            const bool bad = (cs.r == 0xFFFFFFFFu) ? spec_group<true>(cs, src, slot, tops + g * G, lane)
+                                                    : spec_group<false>(cs, src, slot, tops + g * G, lane);
             if (__builtin_expect(bad, 0)) {
                 cs = cs0;
                 src = src0;
