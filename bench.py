@@ -42,7 +42,7 @@ WORKLOADS = {
                 name='L3C cr.cf (3 scales, seed-0 default init), %d x 3x512x512 uint8 noise images per GPU, '
                      'encode+decode round trip, byte-compatible .l3c containers'),
     'rgb_shared': dict(cfg='cr_rgb_shared', n_img=32, H=256, W=256, precision='f16x2', golden='rgbs_256x256',
-                       flop_per_px=1.309e6,
+                       flop_per_px=1.309e6, lanes=1,    # its decode is short (25 ms): more lanes only take SMs away
                        name='RGB-shared baseline cr_rgb_shared.cf (bicubic thumbnail + 1 scale), %d x 3x256x256 '
                             'uint8 noise images per GPU, encode+decode round trip'),
     'crops': dict(cfg='cr', n_img=1, H=3000, W=2000, precision='f16', golden=None, flop_per_px=2.230e6,
@@ -324,6 +324,8 @@ def run_ours(args):
     # decode -- lie inside the timed region.
     # args.lanes decodes are in flight at any time (each on its own set of streams; the range decoders of all
     # of them share one group of SMs), and two encodes are queued ahead on the lowest-priority stream.
+    if args.lanes is None:
+        args.lanes = int(os.environ.get('L3C_BENCH_LANES', wl.get('lanes', 4)))
     n_lanes = max(1, args.lanes)
     lanes, side_stream = codec.lanes(dev, 3 * n_units, n_lanes)[:2] if args.pipeline else (None, None)
     enc_streams = codec.encode_streams(dev, 3 * n_units, n_lanes) if args.pipeline else None
@@ -818,8 +820,8 @@ def main():
     ap.add_argument('--no-tiled', action='store_true', help='skip the extra tiled-layout measurement')
     ap.add_argument('--no-comparators', action='store_true',
                     help='skip the cuDNN timings of the roofline shape (their autotuning floods a profiler capture)')
-    ap.add_argument('--lanes', type=int, default=int(os.environ.get('L3C_BENCH_LANES', 4)),
-                    help='decodes in flight in the pipelined mode (default 4)')
+    ap.add_argument('--lanes', type=int, default=None,
+                    help='decodes in flight in the pipelined mode (default: 4; rgb_shared: 1)')
     ap.add_argument('--no-pipeline', dest='pipeline', action='store_false',
                     help='strictly sequential steps: encode(k), decode(k), encode(k+1), ...')
     args = ap.parse_args()
