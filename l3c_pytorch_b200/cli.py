@@ -87,7 +87,8 @@ def main(argv=None):
     p = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     p.add_argument('--config', default='cr', help='cr | cr_rgb_shared | cr_rgb or a path to a .cf file')
     p.add_argument('--ckpt', default=None, help="checkpoint with {'net': state_dict}")
-    p.add_argument('--precision', default=None, choices=['fp32', 'tf32'])
+    p.add_argument('--precision', default=None, choices=['fp32', 'tf32', 'f16', 'f16x2'],
+                   help='conv mode (default fp32; encoder and decoder must use the same one)')
     sub = p.add_subparsers(dest='mode', required=True)
     e = sub.add_parser('enc')
     e.add_argument('img')
