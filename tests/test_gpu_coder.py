@@ -283,3 +283,72 @@ def test_pack_streams_copies_streams_longer_than_4_MiB():
     for t, n, o in zip(srcs, lens, offs):
         assert torch.equal(blob[int(o):int(o + n)], t[:int(n)])
     assert int(blob[int(offs[0] + lens[0]):int(offs[1])].sum()) == 0      # gaps untouched
+
+
+def test_power_of_two_uniform_rows_keep_the_full_span():
+    """Under the uniform prior at L = 256 every symbol takes exactly 2^-8 of the interval and renormalises by exactly 8
+    bits: the coder's span stays 2^32 (r + 1 wraps to 0) for the whole stream.  The L = 256 decoder runs such groups
+    through its second copy of the speculative loop (range_coder.cu spec_group<true>); a group in which the stream
+    leaves that state is replayed on the exact path.  Streams: all-uniform rows (shared row, pitch 0, like the
+    uniform-prior scale), uniform then random rows (the transition falls inside a group), random then uniform, and
+    blocks of both; decoded in chunks; bytes against the CPU oracle."""
+    from l3c_pytorch_b200 import engine as E, _lib
+    rng = np.random.default_rng(11)
+    dev = torch.device('cuda')
+    L, pitch = 256, 256
+    uni = (np.arange(L + 1, dtype=np.int64) * 256).astype(np.uint16)           # entry 256 = 65536 -> 0
+
+    def table(n, pattern):
+        cdf = _random_table(rng, n, L, True)
+        cdf[pattern] = uni
+        return cdf
+
+    n_list = [1500, 1203, 900, 2001, 64, 9]
+    idx = [np.arange(n) for n in n_list]
+    pats = [np.ones(n_list[0], bool), idx[1] < 101, idx[2] >= 333, (idx[3] // 5) % 2 == 0, np.ones(n_list[4], bool),
+            np.ones(n_list[5], bool)]
+    tables = [table(n, p) for n, p in zip(n_list, pats)]
+    syms = [rng.integers(0, L, size=n).astype(np.int16) for n in n_list]
+    wants = [ac.encode(t, s) for t, s in zip(tables, syms)]
+    ivs = []
+    for t, s, n in zip(tables, syms, n_list):
+        lo = t[np.arange(n), s].astype(np.int64)
+        hi = np.where(s == L - 1, 65536, t[np.arange(n), np.minimum(s + 1, L)].astype(np.int64))
+        ivs.append((lo | ((hi - 1) << 16)).astype(np.uint32))
+    n_streams = len(n_list)
+    lens_sym = np.array(n_list)
+    iv_all = torch.from_numpy(np.concatenate(ivs).view(np.int32)).to(dev)
+    caps = [((n * 17 + 7) // 8 + 64 + 3) & ~3 for n in n_list]
+    slots = torch.zeros(sum(caps), dtype=torch.uint8, device=dev)
+    desc = np.zeros(n_streams, dtype=_lib.ENC_STREAM_DTYPE)
+    starts = np.concatenate([[0], np.cumsum(lens_sym)[:-1]])
+    desc['intervals'] = iv_all.data_ptr() + 4 * starts
+    desc['out'] = slots.data_ptr() + np.concatenate([[0], np.cumsum(caps)[:-1]])
+    desc['n_sym'] = lens_sym
+    desc['out_cap'] = caps
+    desc_dev, lens_dev = E.ac_encode_streams(desc, dev)
+    lens = lens_dev.cpu().numpy()
+    hb = slots.cpu().numpy()
+    for i in range(n_streams):
+        assert hb[desc['out'][i] - slots.data_ptr():][:lens[i]].tobytes() == wants[i], i
+    assert abs(int(lens[0]) - 1500) <= 8                                    # 8 bits per symbol, exactly
+    tab = np.zeros((int(lens_sym.sum()), pitch), np.uint16)
+    tab[:, :L] = np.concatenate(tables)[:, :L]
+    tab_dev = torch.from_numpy(tab.view(np.int16)).to(dev)
+    out = torch.zeros(int(lens_sym.sum()), dtype=torch.uint8, device=dev)
+    state = torch.zeros(n_streams * 4, dtype=torch.int32, device=dev)
+    dd = np.zeros(n_streams, dtype=_lib.DEC_STREAM_DTYPE)
+    dd['table'] = tab_dev.data_ptr() + starts * pitch * 2
+    dd['row_pitch'] = pitch
+    dd['row_pitch'][0] = 0                                                  # stream 0: ONE shared row
+    dd['in'] = desc['out']
+    dd['sym_out'] = out.data_ptr() + starts
+    dd['state'] = state.data_ptr() + 16 * np.arange(n_streams)
+    dd['n_sym'] = lens_sym
+    dd['in_len'] = lens
+    ddev = E.ac_decode_streams(dd, dev, L, 0, 100)
+    E.ac_decode_streams(dd, dev, L, 100, 837, desc_dev=ddev)
+    E.ac_decode_streams(dd, dev, L, 937, 5000, desc_dev=ddev)
+    got = out.cpu().numpy()
+    for i in range(n_streams):
+        assert (got[starts[i]:starts[i] + n_list[i]] == syms[i]).all(), i
