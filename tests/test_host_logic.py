@@ -350,3 +350,42 @@ def test_f16x2_split_weight_images():
             want = wd.reshape(cout, nch, 64).permute(1, 0, 2).double()
         np.testing.assert_allclose(val[:, :cout].numpy(), want.numpy(), rtol=2.0 ** -20, atol=1e-9)
         assert bool((img[:, cout:] == 0).all())
+
+
+def test_f16x2_split_product_model():
+    """Numerics of precision mode 'f16x2' in numpy (what conv_f16x2.cu's three MMAs compute): with
+    x = hi_x + lo_x / 2^11 and w = hi_w + lo_w / 2^11 (all four FP16), a K = 576 dot product evaluated as
+    sum(hi_x hi_w) + sum(hi_x lo_w + lo_x hi_w) / 2^11 with fp32 accumulation is within a few fp32 roundings of the
+    float64 result -- ~1000x closer than the one-MMA FP16-operand mode, whose error is the operand rounding."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    K, n = 576, 4000
+    x = rng.standard_normal((n, K)).astype(np.float32)
+    w = (rng.uniform(-1, 1, (n, K)) / 24).astype(np.float32)
+    want = (x.astype(np.float64) * w.astype(np.float64)).sum(1)
+
+    def split(a):
+        hi = a.astype(np.float16)
+        lo = ((a - hi.astype(np.float32)) * np.float32(2048)).astype(np.float16)
+        return hi.astype(np.float32), lo.astype(np.float32)
+
+    def acc32(p):                      # fp32 accumulation in K order (the tensor core's order is not specified:
+        s = np.zeros(p.shape[0], np.float32)          # any order stays inside the bound asserted below)
+        for k in range(p.shape[1]):
+            s = s + p[:, k]
+        return s
+
+    hx, lx = split(x)
+    hw, lw = split(w)
+    acc1 = acc32(hx * hw)                                                   # products of FP16 pairs are exact in fp32
+    acc2 = acc32(hx * lw) + acc32(lx * hw)
+    got = acc1 + acc2 * np.float32(1.0 / 2048)
+    one = acc32(hx * hw)                                                    # the fast mode: hi parts only
+    f32 = acc32(x * w)
+    scale = np.abs(x.astype(np.float64) * w).sum(1)                         # condition-free error scale
+    e_split = np.abs(got - want) / scale
+    e_one = np.abs(one - want) / scale
+    e_f32 = np.abs(f32 - want) / scale
+    assert e_split.max() < 4e-7, e_split.max()
+    assert e_split.max() < 6 * e_f32.max()                                  # fp32-class
+    assert np.median(e_one) > 200 * np.median(e_split)
