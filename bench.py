@@ -176,6 +176,10 @@ def cpu_roundtrips(workload, n_tasks, n_warm, first_seed=0):
     workers = max(1, min(8, cores // 8, n_tasks))
     threads = max(1, cores // workers)
     ctx = mp.get_context('spawn')
+    # fixed thread teams in the workers: with dynamic teams (the OpenMP / MKL default under oversubscription) a conv
+    # may be split differently in the encoder-side and the decoder-side pass of the same image
+    os.environ.setdefault('OMP_DYNAMIC', 'FALSE')
+    os.environ.setdefault('MKL_DYNAMIC', 'FALSE')
     with ctx.Pool(workers, initializer=_ref_init, initargs=(threads,)) as pool:
         if n_warm:
             pool.map(_ref_roundtrip, [(workload, first_seed + i, h, w) for i in range(n_warm)])
